@@ -1,0 +1,152 @@
+/* p2b.h -- C ABI of the B200 compute core for the phase2-bn254 contribution hot path.
+ *
+ * The reference (kobigurk/phase2-bn254, Rust) has no FFI for this path: the hot loop is a nested
+ * `fn batch_exp` inside each entry point.  This header is the boundary a Rust shim binds with
+ * `extern "C"` (INTEGRATION.md shows the shim); every entry point names the reference code it replaces.
+ *
+ *   level 1  p2b_g{1,2}_batch_mul          -> body of batch_exp, phase2/src/parameters.rs:424-470
+ *            p2b_g{1,2}_batch_mul_powers   -> tau-power generation + batch_exp,
+ *                                             powersoftau/src/batched_accumulator.rs:1130-1181,1201-1229
+ *   level 2  p2b_pot_transform             -> chunk loops of BatchedAccumulator::transform,
+ *                                             powersoftau/src/batched_accumulator.rs:1187-1289
+ *            p2b_phase2_contribute         -> MPCParameters::contribute on the serialized parameters,
+ *                                             phase2/src/parameters.rs:414-522 (+ read/write 663-703)
+ *   benches  p2b_g{1,2}_msm                -> multiexp / dense_multiexp, bellman/src/multiexp.rs:330-475
+ *            p2b_fr_fft                    -> EvaluationDomain::{fft,ifft,coset_fft,icoset_fft},
+ *                                             bellman/src/domain.rs:154-205
+ *
+ * Conventions
+ *   - All buffers are caller-owned; the library borrows them for the duration of the call.
+ *   - Plain entry points take HOST pointers (pageable or pinned) and do their own H2D/D2H.
+ *     `_dev` entry points take DEVICE pointers on the ctx's GPU and run on p2b_stream(ctx).
+ *   - Points use the reference's wire encodings (pairing/src/bn256/ec.rs:763-946,1136-1344):
+ *     P2B_ENC_UNCOMPRESSED (G1 64 B x||y, G2 128 B x.c1||x.c0||y.c1||y.c0, big-endian),
+ *     P2B_ENC_COMPRESSED (32 / 64 B, bit 7 of byte 0 = y is the larger root), bit 6 of byte 0 = infinity;
+ *     P2B_ENC_RAW_MONT_LE = RawEncodable::into_raw_uncompressed_le (ec.rs:653-706; G1: 64 B of
+ *     Montgomery limbs, little-endian, all-zero = infinity; G2: same layout over x.c0,x.c1,y.c0,y.c1).
+ *   - Scalars are 32-byte big-endian canonical values (< r) = `into_repr().write_be()`.
+ *   - Calls are blocking; one ctx is single-caller (not re-entrant); one ctx per GPU.
+ *   - Return value: P2B_OK or a P2B_E* code; p2b_last_error() / p2b_error_detail() describe it.
+ */
+#ifndef P2B_H
+#define P2B_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct p2b_ctx p2b_ctx;
+
+enum {
+    P2B_OK = 0,
+    P2B_EARG = 1,          /* size / argument mismatch (the bins' length panics, compute_constrained.rs:96-102) */
+    P2B_EDECODE = 2,       /* GroupDecodingError (pairing/src/lib.rs:280-291); sub-code in p2b_error_detail */
+    P2B_EINFINITY_IN = 3,  /* DeserializationError::PointAtInfinity (batched_accumulator.rs:987-991) */
+    P2B_EINFINITY_OUT = 4, /* "your contribution happened to produce a point at infinity" (:1176-1179) */
+    P2B_ECUDA = 5          /* CUDA failure */
+};
+enum { /* decode sub-codes */
+    P2B_DEC_NOT_ON_CURVE = 1,
+    P2B_DEC_COORDINATE = 2,
+    P2B_DEC_UNEXPECTED_INFORMATION = 3,
+    P2B_DEC_UNEXPECTED_COMPRESSION_MODE = 4
+};
+enum { P2B_ENC_UNCOMPRESSED = 0, P2B_ENC_COMPRESSED = 1, P2B_ENC_RAW_MONT_LE = 2 };
+enum { /* flags */
+    P2B_CHECK_INPUT = 1,     /* CheckForCorrectness::Yes: is_on_curve on every decoded point */
+    P2B_REJECT_INFINITY = 2  /* infinity in the input or the output is an error (phase-1 semantics) */
+};
+
+/* ---- context ---- */
+int p2b_init(int device, p2b_ctx **out);
+void p2b_destroy(p2b_ctx *ctx);
+const char *p2b_last_error(p2b_ctx *ctx);
+/* index of the first failing element and the decode sub-code of the last error */
+void p2b_error_detail(p2b_ctx *ctx, uint64_t *index, int *sub);
+/* cudaStream_t the ctx launches on (for event timing by the caller) */
+void *p2b_stream(p2b_ctx *ctx);
+/* number of kernels this ctx has launched so far */
+uint64_t p2b_launch_count(p2b_ctx *ctx);
+const char *p2b_version(void);
+
+/* ---- level 1: batch_exp ---- */
+/* out[i] = [s_i] in[i];  n_scalars == n (one per point) or 1 (broadcast, phase-2 shape). */
+int p2b_g1_batch_mul(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *scalars_be32,
+                     size_t n_scalars, int in_enc, int out_enc, int flags);
+int p2b_g2_batch_mul(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *scalars_be32,
+                     size_t n_scalars, int in_enc, int out_enc, int flags);
+/* out[i] = [tau^(start_index + i) * coeff] in[i]  (coeff may be NULL = 1). */
+int p2b_g1_batch_mul_powers(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, const uint8_t tau_be[32],
+                            const uint8_t *coeff_be_or_null, uint64_t start_index, int in_enc, int out_enc, int flags);
+int p2b_g2_batch_mul_powers(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, const uint8_t tau_be[32],
+                            const uint8_t *coeff_be_or_null, uint64_t start_index, int in_enc, int out_enc, int flags);
+/* device-pointer variants (inputs/outputs resident in HBM; async on p2b_stream until p2b_sync) */
+int p2b_g1_batch_mul_dev(p2b_ctx *ctx, const void *d_in, void *d_out, size_t n, const uint8_t *scalars_be32_host,
+                         size_t n_scalars, int in_enc, int out_enc, int flags);
+int p2b_g2_batch_mul_dev(p2b_ctx *ctx, const void *d_in, void *d_out, size_t n, const uint8_t *scalars_be32_host,
+                         size_t n_scalars, int in_enc, int out_enc, int flags);
+int p2b_g1_batch_mul_powers_dev(p2b_ctx *ctx, const void *d_in, void *d_out, size_t n, const uint8_t tau_be[32],
+                                const uint8_t *coeff_be_or_null, uint64_t start_index, int in_enc, int out_enc,
+                                int flags);
+int p2b_g2_batch_mul_powers_dev(p2b_ctx *ctx, const void *d_in, void *d_out, size_t n, const uint8_t tau_be[32],
+                                const uint8_t *coeff_be_or_null, uint64_t start_index, int in_enc, int out_enc,
+                                int flags);
+/* waits for the stream and returns the status of the work queued by _dev calls since the last sync */
+int p2b_sync(p2b_ctx *ctx);
+
+/* ---- level 2: whole entry points on the reference's file formats ---- */
+/* powersoftau geometry (powersoftau/src/parameters.rs:72-120): size of the accumulator part of a file
+ * = hash(64) + all points; the response file additionally carries the 768-byte public key. */
+uint64_t p2b_pot_accumulator_size(uint32_t size_log2, int compressed);
+/* Writes the accumulator region [64, accumulator_size(out)) of `response` exactly as write_chunk would.  Bytes [0,64)
+ * (hash of the challenge) and the trailing public key stay with the caller (compute_constrained.rs:155-161,207-209).
+ * [shard_index, shard_count): this process transforms only its contiguous share of every section (one process per
+ * GPU; shards write disjoint byte ranges of `response`); pass 0, 1 for the whole file. */
+int p2b_pot_transform(p2b_ctx *ctx, const uint8_t *challenge, uint64_t challenge_len, uint8_t *response,
+                      uint64_t response_len, uint32_t size_log2, uint32_t batch_size, int in_compressed,
+                      int out_compressed, int check_input, const uint8_t tau_be[32], const uint8_t alpha_be[32],
+                      const uint8_t beta_be[32], uint32_t shard_index, uint32_t shard_count);
+/* MPCParameters::contribute over the serialized parameters (`MPCParameters::write` format).  The RNG-derived values
+ * are inputs: delta (Fr), s (G1 uncompressed, = G1::rand) and r (G2 uncompressed, = hash_to_g2(transcript) -- the
+ * caller computes it from p2b_phase2_transcript).  params_out must hold params_len + 384 bytes.  Returns the
+ * 64-byte contribution hash (Blake2b-512 of the new public key) in hash_out. */
+int p2b_phase2_transcript(p2b_ctx *ctx, const uint8_t *params, uint64_t params_len, const uint8_t delta_be[32],
+                          const uint8_t s_g1[64], uint8_t transcript_out[64]);
+int p2b_phase2_contribute(p2b_ctx *ctx, const uint8_t *params, uint64_t params_len, uint8_t *params_out,
+                          uint64_t params_out_len, const uint8_t delta_be[32], const uint8_t s_g1[64],
+                          const uint8_t r_g2[128], uint8_t hash_out[64]);
+
+/* ---- Pippenger MSM ---- */
+/* out = sum scalars[i] * points[i]; points uncompressed wire, out uncompressed wire (64 / 128 B). */
+int p2b_g1_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32, size_t n, uint8_t *out);
+int p2b_g2_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32, size_t n, uint8_t *out);
+int p2b_g1_msm_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n, uint8_t *out_host);
+int p2b_g2_msm_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n, uint8_t *out_host);
+/* multi-GPU: each rank computes the partial of its point range as a projective point in raw form
+ * (3 coordinates, Montgomery LE; 96 B G1 / 192 B G2), ranks exchange partials (NCCL all-gather by the
+ * caller), and every rank sums them locally into the final affine result. */
+int p2b_g1_msm_partial_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n,
+                           uint8_t partial_out_host[96]);
+int p2b_g2_msm_partial_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n,
+                           uint8_t partial_out_host[192]);
+int p2b_g1_sum_partials(p2b_ctx *ctx, const uint8_t *partials, size_t count, uint8_t out[64]);
+int p2b_g2_sum_partials(p2b_ctx *ctx, const uint8_t *partials, size_t count, uint8_t out[128]);
+
+/* ---- Fr radix-2 FFT ---- */
+/* In-place, natural order in and out, 2^log_n scalars of 32 BE bytes; inverse => ifft (x m^-1);
+ * coset => coset_fft / icoset_fft with the multiplicative generator 7. */
+int p2b_fr_fft(p2b_ctx *ctx, uint8_t *data, uint32_t log_n, int inverse, int coset);
+int p2b_fr_fft_dev(p2b_ctx *ctx, void *d_data, uint32_t log_n, int inverse, int coset);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,294 @@
+// batch_mul_impl.cuh -- K1/K2/K3/K7: batched independent scalar multiplication out[i] = [k_i] in[i] on sm_100a.
+//
+// GPU replacement for the reference's `batch_exp` closures
+// (powersoftau/src/batched_accumulator.rs:1130-1181 with the tau-power generation of :1201-1216, and
+// phase2/src/parameters.rs:424-470) fused with the chunk codec around them (read_points_chunk :889-1001,
+// write_point :1052-1093).
+//
+// Pipeline per call (all on ctx->stream):
+//   [k_decompress]   compressed wire -> raw affine Montgomery (sqrt per point; only for compressed input)
+//   [k_pow_tables]   4 x 1024 table of tau^(e << 10t) (x coeff) so that tau^i costs 3 Fr mults per lane
+//   k_batch_mul      one thread per point: decode (BE -> limbs -> Montgomery), scalar (array / broadcast /
+//                    tau^(start+i)*coeff), [k]P by GLV + signed fixed windows (smul.cuh), Jacobian result to HBM
+//   k_normalize      Montgomery-trick batched inversion (1 Fermat inversion per ~32 points), affine conversion,
+//                    canonical compare for the sign bit, BE encode -- the reference's batch_normalization
+//                    (ec.rs:251-299) + into_affine + into_compressed (ec.rs:920-945)
+//
+// Data layout in HBM: wire encodings are arrays-of-structs exactly as in the files (64/128/32/64 B per point);
+// a warp reads/writes one contiguous 1-4 KB span.  Jacobian intermediates are structure-of-arrays (X[n], Y[n],
+// Z[n], 32 or 64 B per element) so that consecutive lanes touch consecutive 32 B sectors.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include "codec.cuh"
+#include "p2b_internal.h"
+#include "smul.cuh"
+
+namespace p2b {
+
+// ------------------------------------------------------------------------------------------------- helpers
+template <int NW> __device__ __forceinline__ void load_words(uint32_t *dst, const uint32_t *src) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int i = 0; i < NW / 4; i++) {
+        uint4 v = __ldg(s + i);
+        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+    }
+}
+template <int NW> __device__ __forceinline__ void store_words(uint32_t *dst, const uint32_t *src) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < NW / 4; i++) d[i] = make_uint4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+}
+template <class F> __device__ __forceinline__ F load_elem(const uint32_t *base, size_t i) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    uint32_t w[W];
+    load_words<W>(w, base + i * W);
+    F r;
+#pragma unroll
+    for (int j = 0; j < W; j++) set_word(r, j, w[j]);
+    return r;
+}
+template <class F> __device__ __forceinline__ void store_elem(uint32_t *base, size_t i, const F &v) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    uint32_t w[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) w[j] = get_word(v, j);
+    store_words<W>(base + i * W, w);
+}
+__device__ __forceinline__ void report(unsigned long long *err, uint64_t index, int kind, int sub) {
+    atomicMin(err, (unsigned long long)((index << 8) | ((uint64_t)kind << 4) | (uint64_t)sub));
+}
+
+// slow generic path kept out of line so it does not weigh on the fast path's registers
+template <class F> __device__ __noinline__ void mul_binary_slow(Jac<F> *out, const Aff<F> *p, const uint32_t *k) {
+    uint32_t kk[8];
+    for (int i = 0; i < 8; i++) kk[i] = k[i];
+    *out = mul_binary<F>(*p, kk);
+}
+
+// ------------------------------------------------------------------------------------------------- tau tables
+// tables[t][e] = tau^(e << (10 t)) for t = 0..3, e = 0..1023 (Montgomery Fr); table 3 is pre-multiplied by coeff.
+static __global__ void k_pow_tables(Fr *tables, const uint32_t *tau_canon, const uint32_t *coeff_canon) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 4096) return;
+    int t = j >> 10;
+    uint64_t e = (uint64_t)(j & 1023) << (10 * t);
+    Fr tau, coeff;
+    for (int i = 0; i < 8; i++) { tau.l[i] = tau_canon[i]; coeff.l[i] = coeff_canon[i]; }
+    Fr v = pow_u64(to_mont(tau), e);
+    if (t == 3) v = mul(v, to_mont(coeff));
+    tables[j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------- decompress
+struct DecompressParams {
+    const uint32_t *in;     // compressed wire
+    uint32_t *out;          // raw affine Montgomery LE (x || y), all-zero = infinity
+    size_t n;
+    unsigned long long *err;
+    uint64_t err_base;
+};
+template <class F> __global__ void __launch_bounds__(128) k_decompress(DecompressParams p) {
+    constexpr int WC = Wire<F>::WORDS_COMPRESSED, WU = Wire<F>::WORDS_UNCOMPRESSED;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[WC];
+        load_words<WC>(w, p.in + i * WC);
+        Aff<F> a;
+        bool inf;
+        int rc = point_decode<F>(a, inf, w, ENC_COMPRESSED, false);
+        if (rc) { report(p.err, p.err_base + i, P2B_EDECODE, rc); inf = true; }
+        uint32_t o[WU];
+        point_encode<F>(o, a, inf, ENC_RAW_MONT_LE);
+        store_words<WU>(p.out + i * WU, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- the hot kernel
+struct BatchMulParams {
+    const uint32_t *in;
+    uint32_t *jx, *jy, *jz;
+    size_t n;
+    int in_enc;       // ENC_UNCOMPRESSED or ENC_RAW_MONT_LE
+    int flags;
+    int sc_mode;
+    const uint32_t *scalars;   // mode 0: n x 8 words (BE bytes)
+    uint32_t k[8];             // mode 1
+    const Fr *tables;          // mode 2
+    uint64_t start;            // mode 2
+    unsigned long long *err;
+    uint64_t err_base;
+};
+
+template <class F, int BLOCK> __global__ void __launch_bounds__(BLOCK, 1) k_batch_mul(BatchMulParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
+    constexpr bool IS_G1 = FieldTraits<F>::WORDS == 8;
+    const int tid = threadIdx.x;
+    StridedTable<F> tbl{smem + tid, BLOCK};     // private column: no barriers needed anywhere in this kernel
+    const size_t ntiles = (p.n + BLOCK - 1) / BLOCK;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t i = tile * BLOCK + tid;
+        if (i >= p.n) continue;
+        // ---- point ----
+        uint32_t w[WU];
+        load_words<WU>(w, p.in + i * WU);
+        Aff<F> a;
+        bool inf;
+        int rc = point_decode<F>(a, inf, w, p.in_enc, false);
+        bool oncurve = true;
+        if (!rc && !inf && (IS_G1 || (p.flags & P2B_CHECK_INPUT))) oncurve = on_curve(a);
+        if (!rc && !oncurve && (p.flags & P2B_CHECK_INPUT)) rc = DEC_NOT_ON_CURVE;
+        if (rc) { report(p.err, p.err_base + i, P2B_EDECODE, rc); inf = true; }
+        else if (inf && (p.flags & P2B_REJECT_INFINITY)) report(p.err, p.err_base + i, P2B_EINFINITY_IN, 0);
+        // ---- scalar (canonical little-endian limbs) ----
+        uint32_t k[8];
+        if (p.sc_mode == 0) {
+            uint32_t sw[8];
+            load_words<8>(sw, p.scalars + i * 8);
+            Fr kc = limbs_from_be_words<FrP>(sw);
+            if (!is_canonical(kc)) report(p.err, p.err_base + i, P2B_EARG, 0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = kc.l[j];
+        } else if (p.sc_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = p.k[j];
+        } else {
+            uint64_t e = p.start + i;
+            Fr v = p.tables[e & 1023];
+            v = mul(v, p.tables[1024 + ((e >> 10) & 1023)]);
+            v = mul(v, p.tables[2048 + ((e >> 20) & 1023)]);
+            v = mul(v, p.tables[3072 + ((e >> 30) & 1023)]);
+            v = from_mont(v);
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = v.l[j];
+        }
+        // ---- [k]P ----
+        Jac<F> r;
+        if (inf) {
+            r = jac_infinity<F>();
+        } else {
+            F zr[8];
+            bool bad = !oncurve;      // G1 off-curve garbage (unchecked mode): GLV does not apply
+            if (!bad) {
+                if constexpr (IS_G1) r = g1_mul_glv(a, k, tbl, zr, bad);
+                else r = mul_window4<F>(a, k, tbl, zr, bad);
+            }
+            if (bad) mul_binary_slow<F>(&r, &a, k);
+        }
+        store_elem<F>(p.jx, i, r.x);
+        store_elem<F>(p.jy, i, r.y);
+        store_elem<F>(p.jz, i, r.z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- normalize + encode
+struct NormalizeParams {
+    const uint32_t *jx, *jy, *jz;
+    uint32_t *prefix;     // n elements of F scratch
+    uint32_t *out;        // wire
+    size_t n;
+    int out_enc;
+    int flags;
+    unsigned long long *err;
+    uint64_t err_base;
+};
+template <class F> __global__ void __launch_bounds__(128) k_normalize(NormalizeParams p) {
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    // forward: prefix products of the finite Z's of this thread's strided chunk
+    F acc = FieldTraits<F>::one();
+    size_t last = t;
+    for (size_t i = t; i < p.n; i += T) {
+        F z = load_elem<F>(p.jz, i);
+        store_elem<F>(p.prefix, i, acc);
+        if (!is_zero(z)) acc = mul(acc, z);
+        last = i;
+    }
+    F ai = inv(acc);
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, WC = Wire<F>::WORDS_COMPRESSED;
+    for (size_t i = last;; i -= T) {
+        F z = load_elem<F>(p.jz, i);
+        bool inf = is_zero(z);
+        F pre = load_elem<F>(p.prefix, i);
+        F zinv = mul(ai, pre);
+        if (!inf) ai = mul(ai, z);
+        Aff<F> a;
+        F zi2 = sqr(zinv);
+        a.x = mul(load_elem<F>(p.jx, i), zi2);
+        a.y = mul(load_elem<F>(p.jy, i), mul(zi2, zinv));
+        if (inf && (p.flags & P2B_REJECT_INFINITY)) report(p.err, p.err_base + i, P2B_EINFINITY_OUT, 0);
+        uint32_t o[WU];
+        point_encode<F>(o, a, inf, p.out_enc);
+        if (p.out_enc == ENC_COMPRESSED) store_words<WC>(p.out + i * WC, o);
+        else store_words<WU>(p.out + i * WU, o);
+        if (i < T) break;
+    }
+}
+static constexpr int G1_BLOCK = 256;
+static constexpr int G2_BLOCK = 128;
+
+template <class F, int BLOCK> int launch_typed(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc,
+                                                       int in_enc, int out_enc, int flags, uint64_t err_base) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    constexpr bool IS_G2 = W == 16;
+    const size_t elem = (size_t)W * 4;
+    int rc;
+    if ((rc = dev_reserve(c, c->jac, 3 * n * elem))) return rc;
+    if ((rc = dev_reserve(c, c->prefix, n * elem))) return rc;
+    uint32_t *jx = (uint32_t *)c->jac.p, *jy = jx + n * W, *jz = jy + n * W;
+    const uint32_t *in_words = (const uint32_t *)d_in;
+    int kin_enc = in_enc;
+    if (in_enc == P2B_ENC_COMPRESSED) {
+        if ((rc = dev_reserve(c, c->misc, n * 2 * elem))) return rc;
+        DecompressParams dp{(const uint32_t *)d_in, (uint32_t *)c->misc.p, n, c->d_err, err_base};
+        int blocks = (int)((n + 127) / 128);
+        if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+        k_decompress<F><<<blocks, 128, 0, c->stream>>>(dp);
+        c->launches++;
+        in_words = (const uint32_t *)c->misc.p;
+        kin_enc = ENC_RAW_MONT_LE;
+    }
+    BatchMulParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.in = in_words; bp.jx = jx; bp.jy = jy; bp.jz = jz; bp.n = n; bp.in_enc = kin_enc; bp.flags = flags;
+    bp.sc_mode = sc.mode; bp.err = c->d_err; bp.err_base = err_base;
+    if (sc.mode == 0) bp.scalars = (const uint32_t *)sc.d_scalars;
+    else if (sc.mode == 1) memcpy(bp.k, sc.k, 32);
+    else {
+        if ((rc = dev_reserve(c, c->tables, 4096 * sizeof(Fr) + 64))) return rc;
+        uint32_t *d_tc = (uint32_t *)((char *)c->tables.p + 4096 * sizeof(Fr));
+        uint32_t tc[16];
+        memcpy(tc, sc.tau, 32); memcpy(tc + 8, sc.coeff, 32);
+        P2B_CUDA(c, cudaMemcpyAsync(d_tc, tc, 64, cudaMemcpyHostToDevice, c->stream));
+        k_pow_tables<<<4096 / 128, 128, 0, c->stream>>>((Fr *)c->tables.p, d_tc, d_tc + 8);
+        c->launches++;
+        bp.tables = (const Fr *)c->tables.p;
+        bp.start = sc.start;
+    }
+    const size_t smem = (size_t)BLOCK * 8 * 2 * W * 4;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[IS_G2]) {
+        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[IS_G2] = true;
+    }
+    size_t ntiles = (n + BLOCK - 1) / BLOCK;
+    int grid = (int)(ntiles < (size_t)c->sm_count ? ntiles : (size_t)c->sm_count);
+    if (grid > 0) {
+        k_batch_mul<F, BLOCK><<<grid, BLOCK, smem, c->stream>>>(bp);
+        c->launches++;
+        // ~32 points per thread in the normalisation pass, at least one full wave of 128-thread blocks
+        size_t threads = (n + 31) / 32;
+        if (threads < (size_t)c->sm_count * 128) threads = n < (size_t)c->sm_count * 128 ? n : (size_t)c->sm_count * 128;
+        int nblocks = (int)((threads + 127) / 128);
+        NormalizeParams np{jx, jy, jz, (uint32_t *)c->prefix.p, (uint32_t *)d_out, n, out_enc, flags, c->d_err, err_base};
+        k_normalize<F><<<nblocks, 128, 0, c->stream>>>(np);
+        c->launches++;
+    }
+    P2B_CUDA(c, cudaGetLastError());
+    return P2B_OK;
+}
+
+
+}  // namespace p2b

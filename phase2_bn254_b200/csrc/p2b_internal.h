@@ -1,0 +1,78 @@
+// p2b_internal.h -- context and launcher prototypes shared by the .cu translation units of libp2b.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/p2b.h"
+
+namespace p2b {
+
+// device-side error word: min over (index << 8 | kind << 4 | sub); ~0 = no error
+static constexpr unsigned long long ERR_NONE = ~0ull;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_in = nullptr;      // H2D
+    cudaStream_t copy_out = nullptr;     // D2H
+    int sm_count = 148;
+    std::string last_error;
+    uint64_t err_index = 0;
+    int err_sub = 0;
+    uint64_t launches = 0;
+    unsigned long long *d_err = nullptr;   // device error word
+    unsigned long long *h_err = nullptr;   // pinned mirror
+    // growable device scratch
+    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, fft_tw;
+    // pinned host staging for pageable caller buffers
+    void *h_pin[2] = {nullptr, nullptr};
+    size_t h_pin_cap[2] = {0, 0};
+    cudaEvent_t ev[8] = {};
+    // cached FFT twiddle state
+    uint32_t fft_tw_log_n = 0;
+    int fft_tw_inverse = -1;
+};
+
+int ctx_fail(Ctx *c, int code, const std::string &msg);
+int ctx_cuda(Ctx *c, cudaError_t e, const char *what);
+int dev_reserve(Ctx *c, DevBuf &b, size_t bytes);
+// reads the device error word back (after the stream has drained) and converts it to a P2B_* code
+int ctx_collect_error(Ctx *c);
+
+#define P2B_CUDA(c, call)                                     \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return ctx_cuda((c), e__, #call); \
+    } while (0)
+
+// ---- batch_mul.cu ----
+struct ScalarSpec {
+    int mode;                     // 0 = array (device, 32 B BE each), 1 = broadcast, 2 = powers of tau
+    const void *d_scalars;        // mode 0
+    uint32_t k[8];                // mode 1: canonical little-endian limbs
+    uint32_t tau[8], coeff[8];    // mode 2: canonical limbs (coeff = 1 when absent)
+    uint64_t start;               // mode 2
+};
+// d_in / d_out: device buffers holding n encodings.  Work is queued on c->stream; errors land in c->d_err.
+int launch_batch_mul(Ctx *c, int g2, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc,
+                     int out_enc, int flags, uint64_t err_index_base);
+size_t enc_size(int g2, int enc);
+int read_scalar_be(const uint8_t *be, uint32_t k[8]);   // false if >= r
+
+// ---- msm.cu ----
+int launch_msm(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, void *d_result_jac);
+int msm_finish_affine(Ctx *c, int g2, const void *d_jac, int count, uint8_t *out_host);
+
+// ---- fft.cu ----
+int launch_fr_fft(Ctx *c, void *d_data, uint32_t log_n, int inverse, int coset);
+
+}  // namespace p2b
+
+struct p2b_ctx {
+    p2b::Ctx c;
+};

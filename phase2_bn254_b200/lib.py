@@ -1,0 +1,253 @@
+"""ctypes binding of libp2b.so (include/p2b.h) -- the only way into the compute core from Python.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present, the
+constructors raise.  Buffers are numpy uint8 arrays (host) or raw device pointers (ints).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp2b.so")
+
+OK, EARG, EDECODE, EINFINITY_IN, EINFINITY_OUT, ECUDA = range(6)
+DEC_NOT_ON_CURVE, DEC_COORDINATE, DEC_UNEXPECTED_INFORMATION, DEC_UNEXPECTED_COMPRESSION_MODE = 1, 2, 3, 4
+ENC_UNCOMPRESSED, ENC_COMPRESSED, ENC_RAW_MONT_LE = 0, 1, 2
+CHECK_INPUT, REJECT_INFINITY = 1, 2
+G1, G2 = 0, 1
+
+# every symbol include/p2b.h declares (tests/test_abi.py checks the header and this list agree)
+SYMBOLS = [
+    "p2b_init", "p2b_destroy", "p2b_last_error", "p2b_error_detail", "p2b_stream", "p2b_launch_count",
+    "p2b_version", "p2b_g1_batch_mul", "p2b_g2_batch_mul", "p2b_g1_batch_mul_powers",
+    "p2b_g2_batch_mul_powers", "p2b_g1_batch_mul_dev", "p2b_g2_batch_mul_dev",
+    "p2b_g1_batch_mul_powers_dev", "p2b_g2_batch_mul_powers_dev", "p2b_sync",
+    "p2b_pot_accumulator_size", "p2b_pot_transform", "p2b_phase2_transcript", "p2b_phase2_contribute",
+    "p2b_g1_msm", "p2b_g2_msm", "p2b_g1_msm_dev", "p2b_g2_msm_dev", "p2b_g1_msm_partial_dev",
+    "p2b_g2_msm_partial_dev", "p2b_g1_sum_partials", "p2b_g2_sum_partials", "p2b_fr_fft", "p2b_fr_fft_dev",
+]
+
+
+class P2BError(RuntimeError):
+    """A non-zero return code from the C ABI (code, decode sub-code, first failing element)."""
+
+    def __init__(self, code, message, index=0, sub=0):
+        super().__init__("p2b error %d: %s" % (code, message))
+        self.code, self.index, self.sub = code, index, sub
+
+
+_lib = None
+
+
+def load():
+    """dlopen libp2b.so; raises ImportError when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libp2b.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C phase2_bn254_b200/csrc`")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u8p, sz, u64, i32, u32 = (ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int,
+                                  ctypes.c_uint32)
+    lib.p2b_init.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.p2b_destroy.argtypes = [vp]
+    lib.p2b_destroy.restype = None
+    lib.p2b_last_error.argtypes = [vp]
+    lib.p2b_last_error.restype = ctypes.c_char_p
+    lib.p2b_error_detail.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(i32)]
+    lib.p2b_error_detail.restype = None
+    lib.p2b_stream.argtypes = [vp]
+    lib.p2b_stream.restype = vp
+    lib.p2b_launch_count.argtypes = [vp]
+    lib.p2b_launch_count.restype = u64
+    lib.p2b_version.restype = ctypes.c_char_p
+    for g in ("g1", "g2"):
+        for suffix in ("", "_dev"):
+            getattr(lib, "p2b_%s_batch_mul%s" % (g, suffix)).argtypes = [vp, u8p, u8p, sz, u8p, sz, i32, i32, i32]
+            getattr(lib, "p2b_%s_batch_mul_powers%s" % (g, suffix)).argtypes = [vp, u8p, u8p, sz, u8p, u8p, u64, i32,
+                                                                               i32, i32]
+        if hasattr(lib, "p2b_%s_msm" % g):
+            getattr(lib, "p2b_%s_msm" % g).argtypes = [vp, u8p, u8p, sz, u8p]
+            getattr(lib, "p2b_%s_msm_dev" % g).argtypes = [vp, vp, vp, sz, u8p]
+            getattr(lib, "p2b_%s_msm_partial_dev" % g).argtypes = [vp, vp, vp, sz, u8p]
+            getattr(lib, "p2b_%s_sum_partials" % g).argtypes = [vp, u8p, sz, u8p]
+    lib.p2b_sync.argtypes = [vp]
+    lib.p2b_pot_accumulator_size.argtypes = [u32, i32]
+    lib.p2b_pot_accumulator_size.restype = u64
+    lib.p2b_pot_transform.argtypes = [vp, u8p, u64, u8p, u64, u32, u32, i32, i32, i32, u8p, u8p, u8p, u32, u32]
+    lib.p2b_phase2_transcript.argtypes = [vp, u8p, u64, u8p, u8p, u8p]
+    lib.p2b_phase2_contribute.argtypes = [vp, u8p, u64, u8p, u64, u8p, u8p, u8p, u8p]
+    if hasattr(lib, "p2b_fr_fft"):
+        lib.p2b_fr_fft.argtypes = [vp, u8p, u32, i32, i32]
+        lib.p2b_fr_fft_dev.argtypes = [vp, vp, u32, i32, i32]
+    _lib = lib
+    return lib
+
+
+def enc_size(group, enc):
+    full = 128 if group == G2 else 64
+    return full // 2 if enc == ENC_COMPRESSED else full
+
+
+def _host(buf):
+    """numpy uint8 view of a bytes-like / array (no copy when already contiguous)."""
+    if isinstance(buf, np.ndarray):
+        a = buf if buf.dtype == np.uint8 else buf.view(np.uint8)
+        return np.ascontiguousarray(a).reshape(-1)
+    return np.frombuffer(buf, dtype=np.uint8)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else ctypes.c_void_p(int(a))
+
+
+class Context:
+    """One compute context on one GPU (p2b_init / p2b_destroy)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = ctypes.c_void_p()
+        rc = self.lib.p2b_init(int(device), ctypes.byref(h))
+        if rc != OK:
+            raise P2BError(rc, "p2b_init failed on device %d (no CUDA device / driver?)" % device)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.p2b_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers
+    def _check(self, rc):
+        if rc != OK:
+            idx, sub = ctypes.c_uint64(0), ctypes.c_int(0)
+            self.lib.p2b_error_detail(self.h, ctypes.byref(idx), ctypes.byref(sub))
+            raise P2BError(rc, self.lib.p2b_last_error(self.h).decode(), idx.value, sub.value)
+
+    @property
+    def stream(self):
+        return self.lib.p2b_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return self.lib.p2b_launch_count(self.h)
+
+    def sync(self):
+        self._check(self.lib.p2b_sync(self.h))
+
+    # -- level 1 (host buffers)
+    def batch_mul(self, group, points, scalars, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0, out=None):
+        pts, sc = _host(points), _host(scalars)
+        n = pts.size // enc_size(group, in_enc)
+        if out is None:
+            out = np.empty(max(1, n * enc_size(group, out_enc)), dtype=np.uint8)
+        fn = self.lib.p2b_g2_batch_mul if group == G2 else self.lib.p2b_g1_batch_mul
+        self._check(fn(self.h, _ptr(pts), _ptr(out), n, _ptr(sc), sc.size // 32, in_enc, out_enc, flags))
+        return out[: n * enc_size(group, out_enc)]
+
+    def batch_mul_powers(self, group, points, tau, coeff=None, start=0, in_enc=ENC_UNCOMPRESSED,
+                         out_enc=ENC_UNCOMPRESSED, flags=REJECT_INFINITY, out=None):
+        pts = _host(points)
+        n = pts.size // enc_size(group, in_enc)
+        if out is None:
+            out = np.empty(max(1, n * enc_size(group, out_enc)), dtype=np.uint8)
+        fn = self.lib.p2b_g2_batch_mul_powers if group == G2 else self.lib.p2b_g1_batch_mul_powers
+        t = _host(tau)
+        cf = _host(coeff) if coeff is not None else None
+        self._check(fn(self.h, _ptr(pts), _ptr(out), n, _ptr(t), _ptr(cf) if cf is not None else None, start, in_enc,
+                       out_enc, flags))
+        return out[: n * enc_size(group, out_enc)]
+
+    # -- level 1 (device pointers; asynchronous until sync())
+    def batch_mul_dev(self, group, d_in, d_out, n, scalars, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0):
+        sc = _host(scalars)
+        fn = self.lib.p2b_g2_batch_mul_dev if group == G2 else self.lib.p2b_g1_batch_mul_dev
+        self._check(fn(self.h, _ptr(d_in), _ptr(d_out), n, _ptr(sc), sc.size // 32, in_enc, out_enc, flags))
+
+    def batch_mul_powers_dev(self, group, d_in, d_out, n, tau, coeff=None, start=0, in_enc=ENC_UNCOMPRESSED,
+                             out_enc=ENC_UNCOMPRESSED, flags=REJECT_INFINITY):
+        fn = self.lib.p2b_g2_batch_mul_powers_dev if group == G2 else self.lib.p2b_g1_batch_mul_powers_dev
+        t = _host(tau)
+        cf = _host(coeff) if coeff is not None else None
+        self._check(fn(self.h, _ptr(d_in), _ptr(d_out), n, _ptr(t), _ptr(cf) if cf is not None else None, start, in_enc,
+                       out_enc, flags))
+
+    # -- level 2
+    def pot_accumulator_size(self, size_log2, compressed):
+        return self.lib.p2b_pot_accumulator_size(size_log2, int(compressed))
+
+    def pot_transform(self, challenge, response, size_log2, batch_size, tau, alpha, beta, in_compressed=False,
+                      out_compressed=True, check_input=False, shard_index=0, shard_count=1):
+        ch, rs = _host(challenge), response
+        assert isinstance(rs, np.ndarray) and rs.dtype == np.uint8 and rs.flags.writeable
+        self._check(self.lib.p2b_pot_transform(self.h, _ptr(ch), ch.size, _ptr(rs), rs.size, size_log2, batch_size,
+                                               int(in_compressed), int(out_compressed), int(check_input),
+                                               _ptr(_host(tau)), _ptr(_host(alpha)), _ptr(_host(beta)), shard_index,
+                                               shard_count))
+
+    def phase2_transcript(self, params, delta, s_g1):
+        p = _host(params)
+        out = np.empty(64, dtype=np.uint8)
+        self._check(self.lib.p2b_phase2_transcript(self.h, _ptr(p), p.size, _ptr(_host(delta)), _ptr(_host(s_g1)),
+                                                   _ptr(out)))
+        return out.tobytes()
+
+    def phase2_contribute(self, params, delta, s_g1, r_g2, out=None):
+        p = _host(params)
+        if out is None:
+            out = np.empty(p.size + 384, dtype=np.uint8)
+        h = np.empty(64, dtype=np.uint8)
+        self._check(self.lib.p2b_phase2_contribute(self.h, _ptr(p), p.size, _ptr(out), out.size, _ptr(_host(delta)),
+                                                   _ptr(_host(s_g1)), _ptr(_host(r_g2)), _ptr(h)))
+        return out[: p.size + 384], h.tobytes()
+
+    # -- MSM
+    def msm(self, group, points, scalars):
+        pts, sc = _host(points), _host(scalars)
+        n = sc.size // 32
+        out = np.empty(enc_size(group, ENC_UNCOMPRESSED), dtype=np.uint8)
+        fn = self.lib.p2b_g2_msm if group == G2 else self.lib.p2b_g1_msm
+        self._check(fn(self.h, _ptr(pts), _ptr(sc), n, _ptr(out)))
+        return out.tobytes()
+
+    def msm_dev(self, group, d_points, d_scalars, n):
+        out = np.empty(enc_size(group, ENC_UNCOMPRESSED), dtype=np.uint8)
+        fn = self.lib.p2b_g2_msm_dev if group == G2 else self.lib.p2b_g1_msm_dev
+        self._check(fn(self.h, _ptr(d_points), _ptr(d_scalars), n, _ptr(out)))
+        return out.tobytes()
+
+    def msm_partial_dev(self, group, d_points, d_scalars, n):
+        out = np.empty(192 if group == G2 else 96, dtype=np.uint8)
+        fn = self.lib.p2b_g2_msm_partial_dev if group == G2 else self.lib.p2b_g1_msm_partial_dev
+        self._check(fn(self.h, _ptr(d_points), _ptr(d_scalars), n, _ptr(out)))
+        return out
+
+    def sum_partials(self, group, partials):
+        p = _host(partials)
+        count = p.size // (192 if group == G2 else 96)
+        out = np.empty(enc_size(group, ENC_UNCOMPRESSED), dtype=np.uint8)
+        fn = self.lib.p2b_g2_sum_partials if group == G2 else self.lib.p2b_g1_sum_partials
+        self._check(fn(self.h, _ptr(p), count, _ptr(out)))
+        return out.tobytes()
+
+    # -- FFT
+    def fr_fft(self, data, inverse=False, coset=False):
+        a = np.array(_host(data), dtype=np.uint8, copy=True)
+        n = a.size // 32
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise P2BError(EARG, "fft length must be a power of two")
+        self._check(self.lib.p2b_fr_fft(self.h, _ptr(a), log_n, int(inverse), int(coset)))
+        return a
+
+    def fr_fft_dev(self, d_data, log_n, inverse=False, coset=False):
+        self._check(self.lib.p2b_fr_fft_dev(self.h, _ptr(d_data), log_n, int(inverse), int(coset)))

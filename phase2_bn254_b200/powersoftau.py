@@ -1,0 +1,110 @@
+"""Host-side mirror of the powersoftau crate's contribution interface, backed by libp2b.so.
+
+Mirrors (names, argument meaning, error behaviour):
+  CeremonyParams         powersoftau/src/parameters.rs:38-120
+  UseCompression, CheckForCorrectness   parameters.rs:127-140
+  DeserializationError   parameters.rs:143-170
+  PrivateKey             powersoftau/src/keypair.rs:47-51
+  BatchedAccumulator.transform   powersoftau/src/batched_accumulator.rs:1119-1292
+The maps are numpy uint8 arrays (np.memmap works), exactly the byte layout of the challenge / response files.
+"""
+import hashlib
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _lib
+
+
+class UseCompression:
+    Yes, No = True, False
+
+
+class CheckForCorrectness:
+    Yes, No = True, False
+
+
+class DeserializationError(Exception):
+    """IoError / DecodingError(GroupDecodingError) / PointAtInfinity."""
+
+    def __init__(self, kind, detail=""):
+        super().__init__("%s %s" % (kind, detail))
+        self.kind = kind
+
+
+class CeremonyParams:
+    """Bn256 geometry: g1 64/32 bytes, g2 128/64 bytes (parameters.rs:21-34,72-120)."""
+
+    def __init__(self, size, batch_size):
+        self.size, self.batch_size = size, batch_size
+        self.g1, self.g2, self.g1_compressed, self.g2_compressed = 64, 128, 32, 64
+        self.powers_length = 1 << size
+        self.powers_g1_length = (self.powers_length << 1) - 1
+        self.hash_size = 64
+        self.accumulator_size = (self.powers_g1_length * self.g1 + self.powers_length * self.g2 +
+                                 self.powers_length * self.g1 + self.powers_length * self.g1 + self.g2 +
+                                 self.hash_size)
+        self.public_key_size = 3 * self.g2 + 6 * self.g1
+        self.contribution_size = (self.powers_g1_length * self.g1_compressed +
+                                  self.powers_length * self.g2_compressed +
+                                  self.powers_length * self.g1_compressed +
+                                  self.powers_length * self.g1_compressed + self.g2_compressed + self.hash_size +
+                                  self.public_key_size)
+
+
+@dataclass
+class PrivateKey:
+    """tau, alpha, beta as integers in [0, r) (keypair.rs:47-51)."""
+    tau: int
+    alpha: int
+    beta: int
+
+
+def calculate_hash(input_map):
+    """Blake2b-512 over the whole map (powersoftau/src/utils.rs:20-27)."""
+    h = hashlib.blake2b()
+    a = np.asarray(input_map, dtype=np.uint8).reshape(-1)
+    step = 1 << 26
+    for off in range(0, a.size, step):
+        h.update(a[off: off + step].data)
+    return h.digest()
+
+
+class BatchedAccumulator:
+    """Only `transform` lives on the GPU path; the class is a namespace like the reference's impl block."""
+
+    _ctx = None
+
+    @classmethod
+    def context(cls, device=0):
+        if cls._ctx is None or cls._ctx.device != device:
+            cls._ctx = _lib.Context(device)
+        return cls._ctx
+
+    @classmethod
+    def transform(cls, input_map, output_map, input_is_compressed, compress_the_output,
+                  check_input_for_correctness, key, parameters, ctx=None, shard_index=0, shard_count=1):
+        """Transforms the accumulator with a private key (batched_accumulator.rs:1119-1292).
+
+        Writes output_map[64 : accumulator end]; bytes [0, 64) and the public key tail are the caller's, as in
+        compute_constrained.rs:155-161,207-209.  Raises DeserializationError where the reference's
+        read_chunk(...).expect() panics and AssertionError where it asserts on a produced point at infinity."""
+        ctx = ctx or cls.context()
+        need_in = ctx.pot_accumulator_size(parameters.size, input_is_compressed)
+        if len(input_map) < need_in:
+            raise ValueError("The size of challenge file should be %d, but it's %d" % (need_in, len(input_map)))
+        be = lambda v: np.frombuffer(int(v).to_bytes(32, "big"), dtype=np.uint8)
+        try:
+            ctx.pot_transform(input_map, output_map, parameters.size, parameters.batch_size, be(key.tau),
+                              be(key.alpha), be(key.beta), bool(input_is_compressed), bool(compress_the_output),
+                              bool(check_input_for_correctness), shard_index, shard_count)
+        except _lib.P2BError as e:
+            if e.code == _lib.EDECODE:
+                names = {1: "NotOnCurve", 2: "CoordinateDecodingError", 3: "UnexpectedInformation",
+                         4: "UnexpectedCompressionMode"}
+                raise DeserializationError("DecodingError", "%s at element %d" % (names.get(e.sub, "?"), e.index))
+            if e.code == _lib.EINFINITY_IN:
+                raise DeserializationError("PointAtInfinity", "at element %d" % e.index)
+            if e.code == _lib.EINFINITY_OUT:
+                raise AssertionError("your contribution happened to produce a point at infinity, please re-run")
+            raise

@@ -1,0 +1,102 @@
+"""GPU parity: powersoftau transform and phase2 contribute on the reference's file formats vs the oracle."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from util import G1_GEN, G2_GEN, R_MOD, be, random_points
+
+pytestmark = pytest.mark.gpu
+
+TAU = 0x1111111111111111111111111111111111111111111111111111111111111111 % R_MOD
+ALPHA = 0x2222222222222222222222222222222222222222222222222222222222222222 % R_MOD
+BETA = 0x0333333333333333333333333333333333333333333333333333333333333333 % R_MOD
+
+
+@pytest.mark.parametrize("size,batch", [(3, 4), (6, 16), (10, 256)])
+def test_transform_initial_challenge(ctx, oracle, size, batch):
+    """Config 1: new -> transform on the deterministic initial accumulator; response hash oracle == GPU."""
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey, calculate_hash
+    params = CeremonyParams(size, batch)
+    challenge = oracle.pot_generate_initial(size)
+    assert len(challenge) == params.accumulator_size
+    response = np.zeros(params.contribution_size, dtype=np.uint8)
+    response[:64] = np.frombuffer(calculate_hash(np.frombuffer(challenge, dtype=np.uint8)), dtype=np.uint8)
+    BatchedAccumulator.transform(np.frombuffer(challenge, dtype=np.uint8), response, False, True, False,
+                                 PrivateKey(TAU, ALPHA, BETA), params, ctx=ctx)
+    exp = oracle.pot_transform(challenge, size, batch, be(TAU), be(ALPHA), be(BETA), threads=8)
+    acc_len = params.contribution_size - params.public_key_size
+    assert len(exp) == acc_len
+    assert hashlib.blake2b(response[:acc_len].tobytes()).hexdigest() == hashlib.blake2b(exp).hexdigest()
+
+
+def test_transform_chain_and_modes(ctx, oracle):
+    """Second contribution on a non-trivial accumulator, every compression combination, checked input, 2 shards."""
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    size, batch = 5, 8
+    params = CeremonyParams(size, batch)
+    ch0 = oracle.pot_generate_initial(size)
+    ch1 = oracle.pot_transform(ch0, size, batch, be(TAU), be(ALPHA), be(BETA), out_compressed=False, threads=8)
+    ch1c = oracle.pot_transform(ch0, size, batch, be(TAU), be(ALPHA), be(BETA), out_compressed=True, threads=8)
+    key = PrivateKey(ALPHA, BETA, TAU)
+    for in_c, src in ((False, ch1), (True, ch1c)):
+        for out_c in (False, True):
+            for check in (False, True):
+                exp = oracle.pot_transform(src, size, batch, be(ALPHA), be(BETA), be(TAU), in_c, out_c, check, threads=8)
+                out = np.zeros(len(exp), dtype=np.uint8)
+                # two shards writing disjoint ranges of the same response (the multi-GPU decomposition)
+                for shard in range(2):
+                    BatchedAccumulator.transform(np.frombuffer(src, dtype=np.uint8), out, in_c, out_c, check, key,
+                                                 params, ctx=ctx, shard_index=shard, shard_count=2)
+                assert out[64:].tobytes() == exp[64:], (in_c, out_c, check)
+
+
+def test_transform_rejects_infinity_and_garbage(ctx, oracle):
+    from phase2_bn254_b200.powersoftau import (BatchedAccumulator, CeremonyParams, DeserializationError, PrivateKey)
+    size = 3
+    params = CeremonyParams(size, 4)
+    ch = bytearray(oracle.pot_generate_initial(size))
+    out = np.zeros(params.contribution_size, dtype=np.uint8)
+    bad = bytearray(ch)
+    bad[64 + 2 * 64: 64 + 3 * 64] = bytes([0x40]) + bytes(63)
+    with pytest.raises(DeserializationError) as e:
+        BatchedAccumulator.transform(np.frombuffer(bytes(bad), dtype=np.uint8), out, False, True, False,
+                                     PrivateKey(TAU, ALPHA, BETA), params, ctx=ctx)
+    assert e.value.kind == "PointAtInfinity"
+    with pytest.raises(AssertionError):
+        BatchedAccumulator.transform(np.frombuffer(bytes(ch), dtype=np.uint8), out, False, True, False,
+                                     PrivateKey(TAU, 0, BETA), params, ctx=ctx)      # alpha = 0 -> infinity produced
+    with pytest.raises(ValueError):
+        BatchedAccumulator.transform(np.frombuffer(bytes(ch[:-1]), dtype=np.uint8), out, False, True, False,
+                                     PrivateKey(TAU, ALPHA, BETA), params, ctx=ctx)
+
+
+def synthetic_params(oracle, m, n_contrib=0, seed=5):
+    """A synthetic MPCParameters file: h = m-1 points, l = m points, a/b_g1/b_g2 = 3, ic = 2 (config 3 shape)."""
+    g1 = lambda n, s: random_points(oracle, 0, n, seed + s)
+    g2 = lambda n, s: random_points(oracle, 1, n, seed + s)
+    body = g1(1, 1) + g1(1, 2) + g2(1, 3) + g2(1, 4) + g1(1, 5) + g2(1, 6)
+    for n, s, grp in ((2, 7, 0), (m - 1, 8, 0), (m, 9, 0), (3, 10, 0), (3, 11, 0), (3, 12, 1)):
+        body += struct.pack(">I", n) + (g2(n, s) if grp else g1(n, s))
+    body += hashlib.blake2b(body).digest()
+    contribs = b"".join(g1(1, 20 + i) + g1(1, 30 + i) + g1(1, 40 + i) + g2(1, 50 + i) + hashlib.blake2b(bytes([i])).digest()
+                        for i in range(n_contrib))
+    return body + struct.pack(">I", n_contrib) + contribs
+
+
+@pytest.mark.parametrize("m,n_contrib", [(8, 0), (300, 2)])
+def test_phase2_contribute(ctx, oracle, m, n_contrib):
+    from phase2_bn254_b200.phase2 import MPCParameters
+    buf = synthetic_params(oracle, m, n_contrib)
+    delta = 0x0fedcba987654321fedcba987654321fedcba987654321fedcba987654321 % R_MOD
+    s = random_points(oracle, 0, 1, 77)
+    r = random_points(oracle, 1, 1, 78)
+    exp_file, exp_hash = oracle.phase2_contribute(buf, be(delta), s, r, threads=8)
+    p = MPCParameters.read(buf)
+    got_hash = p.contribute(delta, s, r_g2=r, ctx=ctx)
+    assert got_hash == exp_hash
+    assert p.data.tobytes() == exp_file
+    # a second contribution on top (the contributions list grows)
+    exp2, h2 = oracle.phase2_contribute(exp_file, be(delta + 1), s, r, threads=8)
+    assert p.contribute(delta + 1, s, r_g2=r, ctx=ctx) == h2 and p.data.tobytes() == exp2
