@@ -127,15 +127,11 @@ int p2b_g1_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32,
 int p2b_g2_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32, size_t n, uint8_t *out);
 int p2b_g1_msm_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n, uint8_t *out_host);
 int p2b_g2_msm_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n, uint8_t *out_host);
-/* multi-GPU: each rank computes the partial of its point range as a projective point in raw form
- * (3 coordinates, Montgomery LE; 96 B G1 / 192 B G2), ranks exchange partials (NCCL all-gather by the
- * caller), and every rank sums them locally into the final affine result. */
-int p2b_g1_msm_partial_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n,
-                           uint8_t partial_out_host[96]);
-int p2b_g2_msm_partial_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n,
-                           uint8_t partial_out_host[192]);
-int p2b_g1_sum_partials(p2b_ctx *ctx, const uint8_t *partials, size_t count, uint8_t out[64]);
-int p2b_g2_sum_partials(p2b_ctx *ctx, const uint8_t *partials, size_t count, uint8_t out[128]);
+/* multi-GPU: the MSM shards by point range; each rank's result is an ordinary (affine, uncompressed) point, the
+ * ranks exchange the 64 / 128-byte results (NCCL all-gather by the caller) and every rank adds them locally:
+ * out = sum of `count` uncompressed points (infinity allowed). */
+int p2b_g1_sum_points(p2b_ctx *ctx, const uint8_t *points, size_t count, uint8_t out[64]);
+int p2b_g2_sum_points(p2b_ctx *ctx, const uint8_t *points, size_t count, uint8_t out[128]);
 
 /* ---- Fr radix-2 FFT ---- */
 /* In-place, natural order in and out, 2^log_n scalars of 32 BE bytes; inverse => ifft (x m^-1);

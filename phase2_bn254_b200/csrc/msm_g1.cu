@@ -1,0 +1,83 @@
+// msm_g1.cu -- G1 instantiation of the Pippenger MSM kernels and the MSM entry points of the C ABI.
+#include "msm_impl.cuh"
+
+namespace p2b {
+int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire);
+void launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
+
+// result: uncompressed wire bytes in device memory c->misc (first 128 bytes)
+static int msm_run(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, uint8_t *out_host) {
+    int rc;
+    if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
+    uint32_t *d_out = (uint32_t *)c->misc.p;
+    rc = g2 ? msm_typed_g2(c, d_points, d_scalars, n, d_out) : msm_typed<Fq>(c, d_points, d_scalars, n, d_out);
+    if (rc) return rc;
+    P2B_CUDA(c, cudaMemcpyAsync(out_host, d_out, g2 ? 128 : 64, cudaMemcpyDeviceToHost, c->stream));
+    return ctx_collect_error(c);
+}
+
+static int msm_begin(Ctx *c) {
+    P2B_CUDA(c, cudaSetDevice(c->device));
+    c->last_error.clear();
+    P2B_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream));
+    return P2B_OK;
+}
+
+static int msm_host(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
+    if (!out || (n && (!points || !scalars))) return ctx_fail(c, P2B_EARG, "null buffer");
+    int rc = msm_begin(c);
+    if (rc) return rc;
+    const size_t psz = g2 ? 128 : 64;
+    if ((rc = dev_reserve(c, c->stage_in[0], (n ? n : 1) * psz))) return rc;
+    if ((rc = dev_reserve(c, c->stage_in[1], (n ? n : 1) * 32))) return rc;
+    if (n) {
+        P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[0].p, points, n * psz, cudaMemcpyHostToDevice, c->stream));
+        P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[1].p, scalars, n * 32, cudaMemcpyHostToDevice, c->stream));
+    }
+    return msm_run(c, g2, c->stage_in[0].p, c->stage_in[1].p, n, out);
+}
+static int msm_dev(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) {
+    if (!out || (n && (!d_points || !d_scalars))) return ctx_fail(c, P2B_EARG, "null buffer");
+    int rc = msm_begin(c);
+    if (rc) return rc;
+    return msm_run(c, g2, d_points, d_scalars, n, out);
+}
+static int sum_points(Ctx *c, int g2, const uint8_t *points, size_t count, uint8_t *out) {
+    if (!out || (count && !points)) return ctx_fail(c, P2B_EARG, "null buffer");
+    if (count > 65536) return ctx_fail(c, P2B_EARG, "sum_points: too many points");
+    int rc = msm_begin(c);
+    if (rc) return rc;
+    const size_t psz = g2 ? 128 : 64;
+    if ((rc = dev_reserve(c, c->misc, 4096 + count * psz))) return rc;
+    uint32_t *d_out = (uint32_t *)c->misc.p, *d_in = d_out + 1024;
+    if (count) P2B_CUDA(c, cudaMemcpyAsync(d_in, points, count * psz, cudaMemcpyHostToDevice, c->stream));
+    if (g2) launch_sum_points_g2(c, d_in, (uint32_t)count, d_out);
+    else k_sum_points<Fq><<<1, 32, 0, c->stream>>>(d_in, (uint32_t)count, d_out, c->d_err);
+    c->launches++;
+    P2B_CUDA(c, cudaMemcpyAsync(out, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
+    return ctx_collect_error(c);
+}
+
+}  // namespace p2b
+
+using namespace p2b;
+extern "C" {
+int p2b_g1_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
+    return h ? msm_host(&h->c, 0, points, scalars, n, out) : P2B_EARG;
+}
+int p2b_g2_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
+    return h ? msm_host(&h->c, 1, points, scalars, n, out) : P2B_EARG;
+}
+int p2b_g1_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) {
+    return h ? msm_dev(&h->c, 0, d_points, d_scalars, n, out) : P2B_EARG;
+}
+int p2b_g2_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) {
+    return h ? msm_dev(&h->c, 1, d_points, d_scalars, n, out) : P2B_EARG;
+}
+int p2b_g1_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[64]) {
+    return h ? sum_points(&h->c, 0, points, count, out) : P2B_EARG;
+}
+int p2b_g2_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[128]) {
+    return h ? sum_points(&h->c, 1, points, count, out) : P2B_EARG;
+}
+}

@@ -1,0 +1,386 @@
+// msm_impl.cuh -- K4/K5: Pippenger multi-scalar multiplication sum_i k_i * P_i over BN254 G1 / G2 on sm_100a.
+//
+// GPU replacement for bellman's multiexp / dense_multiexp (bellman/src/multiexp.rs:53-157,330-475; copy in
+// powersoftau/src/utils.rs:190-292).  The result is one group element, so the window width, the bucket layout
+// and the reduction order are free (the reference's `c = ceil(ln n)` is a CPU cache heuristic); only the affine
+// encoding of the sum is observable.
+//
+//   k_msm_prepare     wire points -> affine Montgomery (AoS, 64/128 B), once per call
+//   k_msm_hist        signed c-bit digits of every scalar; histogram of (window, |digit|) with L2 atomics
+//   k_msm_scan        exclusive prefix sum of the histogram -> bucket offsets (counting sort, pass 2)
+//   k_msm_scatter     digits recomputed; (point index, sign) written to its bucket's slot (counting sort, pass 3)
+//   k_msm_accumulate  one thread per bucket: gathers its points (coalescing is impossible by construction; every
+//                     gather is a full 64/128 B point), mixed adds in XYZZ coordinates (8M + 2S)
+//   k_msm_reduce1     per window, 32-bucket strips: running-sum trick -> (sum, weighted sum) per strip
+//   k_msm_reduce2     per window, one block: warp-shuffle suffix scans + shuffle tree reductions combine the strips
+//   k_msm_final       Horner over the windows, one inversion, affine wire encoding
+//
+// Signed digits halve the bucket count: digit d in (-2^(c-1), 2^(c-1)], bucket |d|, sign folded into the point's y.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include "codec.cuh"
+#include "xyzz.cuh"
+#include "p2b_internal.h"
+
+namespace p2b {
+
+// NOTE: the reduction kernels call the inlined adds from as few call sites as possible (every site is ~3k SASS
+// instructions).  An earlier version routed them through __noinline__ wrappers taking pointers to locals; combined
+// with the warp shuffles around the calls that produced wrong sums on sm_100a (see tools/reduce2_test.cu), so the
+// adds are inlined and the kernels are structured as loops over "items" instead.
+template <class F> __device__ __forceinline__ Xyzz<F> xadd(const Xyzz<F> &p, const Xyzz<F> &q) { return xyzz_add(p, q); }
+template <class F> __device__ __forceinline__ Xyzz<F> xdbl(const Xyzz<F> &p) { return xyzz_dbl(p); }
+
+// ------------------------------------------------------------------------------------------------- memory helpers
+template <int NW> __device__ __forceinline__ void ldw(uint32_t *dst, const uint32_t *src) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int i = 0; i < NW / 4; i++) { uint4 v = __ldg(s + i); dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w; }
+}
+template <int NW> __device__ __forceinline__ void stw(uint32_t *dst, const uint32_t *src) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < NW / 4; i++) d[i] = make_uint4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+}
+template <class F> __device__ __forceinline__ void store_xyzz(uint32_t *base, size_t i, const Xyzz<F> &p) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    uint32_t w[4 * W];
+#pragma unroll
+    for (int j = 0; j < W; j++) { w[j] = get_word(p.x, j); w[W + j] = get_word(p.y, j); w[2 * W + j] = get_word(p.zz, j); w[3 * W + j] = get_word(p.zzz, j); }
+    stw<4 * W>(base + i * 4 * W, w);
+}
+template <class F> __device__ __forceinline__ Xyzz<F> load_xyzz(const uint32_t *base, size_t i) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    uint32_t w[4 * W];
+    const uint4 *s = reinterpret_cast<const uint4 *>(base + i * 4 * W);
+#pragma unroll
+    for (int j = 0; j < W; j++) { uint4 v = s[j]; w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
+    Xyzz<F> p;
+#pragma unroll
+    for (int j = 0; j < W; j++) { set_word(p.x, j, w[j]); set_word(p.y, j, w[W + j]); set_word(p.zz, j, w[2 * W + j]); set_word(p.zzz, j, w[3 * W + j]); }
+    return p;
+}
+template <class F> __device__ __forceinline__ Xyzz<F> shfl_xyzz(const Xyzz<F> &p, int src_lane) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    Xyzz<F> r;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        set_word(r.x, j, __shfl_sync(0xffffffffu, get_word(p.x, j), src_lane));
+        set_word(r.y, j, __shfl_sync(0xffffffffu, get_word(p.y, j), src_lane));
+        set_word(r.zz, j, __shfl_sync(0xffffffffu, get_word(p.zz, j), src_lane));
+        set_word(r.zzz, j, __shfl_sync(0xffffffffu, get_word(p.zzz, j), src_lane));
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------- parameters
+struct MsmGeom {
+    uint32_t c;        // window bits
+    uint32_t nwin;     // number of windows
+    uint32_t nb;       // buckets per window = 2^(c-1); bucket ids 1..nb (slot 0 unused)
+    uint32_t nbk;      // nb + 1
+    uint32_t strip;    // buckets per reduce1 thread
+    uint32_t tpw;      // reduce threads per window = nb / strip (multiple of 32, <= 1024)
+};
+__device__ __forceinline__ void scalar_words(uint32_t k[8], const uint32_t *scalars, size_t i) {
+    uint32_t w[8];
+    ldw<8>(w, scalars + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = bswap32(w[7 - j]);
+}
+// raw c-bit window w of k (c <= 16)
+__device__ __forceinline__ uint32_t raw_window(const uint32_t k[8], uint32_t bit, uint32_t c) {
+    uint32_t word = bit >> 5, sh = bit & 31;
+    uint64_t v = k[word];
+    if (word + 1 < 8) v |= (uint64_t)k[word + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+static __device__ __forceinline__ void report_err(unsigned long long *err, uint64_t index, int kind, int sub) {
+    atomicMin(err, (unsigned long long)((index << 8) | ((uint64_t)kind << 4) | (uint64_t)sub));
+}
+
+// ------------------------------------------------------------------------------------------------- kernels
+template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const uint32_t *wire, uint32_t *aff, size_t n, unsigned long long *err) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[WU];
+        ldw<WU>(w, wire + i * WU);
+        Aff<F> a;
+        bool inf;
+        int rc = point_decode<F>(a, inf, w, ENC_UNCOMPRESSED, false);
+        if (rc) { report_err(err, i, P2B_EDECODE, rc); inf = true; }
+        uint32_t o[WU];
+        point_encode<F>(o, a, inf, ENC_RAW_MONT_LE);   // infinity = all-zero: skipped by the accumulator
+        stw<WU>(aff + i * WU, o);
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *hist, unsigned long long *err) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t k[8];
+        scalar_words(k, scalars, i);
+        Fr kc;
+#pragma unroll
+        for (int j = 0; j < 8; j++) kc.l[j] = k[j];
+        if (!is_canonical(kc)) report_err(err, i, P2B_EARG, 0);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < g.nwin; w++) {
+            uint32_t d = raw_window(k, w * g.c, g.c) + carry;
+            carry = d > g.nb;
+            uint32_t b = carry ? (1u << g.c) - d : d;
+            if (b) atomicAdd(&hist[w * g.nbk + b], 1u);
+        }
+    }
+}
+
+// single block: exclusive scan of `count` entries; also copies the offsets into `cursor`
+static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t count) {
+    __shared__ uint32_t sums[1024];
+    const uint32_t t = threadIdx.x, per = (count + 1023) / 1024;
+    const uint32_t lo = t * per, hi = lo + per < count ? lo + per : count;
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += hist[i];
+    sums[t] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t v = t >= d ? sums[t - d] : 0;
+        __syncthreads();
+        sums[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? sums[t - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; cursor[i] = run; run += hist[i]; }
+    if (t == 1023) offsets[count] = sums[1023];
+}
+
+static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *cursor, uint32_t *sorted) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t k[8];
+        scalar_words(k, scalars, i);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < g.nwin; w++) {
+            uint32_t d = raw_window(k, w * g.c, g.c) + carry;
+            carry = d > g.nb;
+            uint32_t b = carry ? (1u << g.c) - d : d;
+            if (b) {
+                uint32_t pos = atomicAdd(&cursor[w * g.nbk + b], 1u);
+                sorted[pos] = ((uint32_t)i << 1) | carry;     // carry == 1 <=> negative digit
+            }
+        }
+    }
+}
+
+template <class F> __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
+                                                                           MsmGeom g, uint32_t *buckets) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
+    const uint32_t total = g.nwin * g.nbk;
+    for (uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += gridDim.x * blockDim.x) {
+        const uint32_t lo = offsets[gb], hi = offsets[gb + 1];
+        Xyzz<F> acc = xyzz_infinity<F>();
+#pragma unroll 1
+        for (uint32_t e = lo; e < hi; e++) {
+            const uint32_t ent = __ldg(sorted + e);
+            uint32_t w[WU];
+            ldw<WU>(w, aff + (size_t)(ent >> 1) * WU);
+            uint32_t any = 0;
+#pragma unroll
+            for (int j = 0; j < WU; j++) any |= w[j];
+            if (!any) continue;                                // point at infinity contributes nothing
+            Aff<F> q;
+#pragma unroll
+            for (int j = 0; j < W; j++) { set_word(q.x, j, w[j]); set_word(q.y, j, w[W + j]); }
+            q.y = cneg(q.y, (ent & 1u) != 0);
+            acc = xyzz_madd(acc, q);
+        }
+        store_xyzz<F>(buckets, gb, acc);
+    }
+}
+
+// thread (w, t): buckets b = t*strip + 1 .. (t+1)*strip, walked from the top:  run = sum B_b ; acc = sum (b - t*strip) B_b
+template <class F> __global__ void __launch_bounds__(128) k_msm_reduce1(const uint32_t *buckets, MsmGeom g, uint32_t *s1, uint32_t *s2) {
+    const uint32_t total = g.nwin * g.tpw;
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    const uint32_t w = id / g.tpw, t = id % g.tpw;
+    Xyzz<F> run = xyzz_infinity<F>(), acc = xyzz_infinity<F>();
+#pragma unroll 1
+    for (uint32_t j = g.strip; j >= 1; j--) {
+        Xyzz<F> b = load_xyzz<F>(buckets, (size_t)w * g.nbk + t * g.strip + j);
+        run = xadd(run, b);
+        acc = xadd(acc, run);
+    }
+    store_xyzz<F>(s1, id, run);
+    store_xyzz<F>(s2, id, acc);
+}
+
+// One warp-wide reduction of 32 XYZZ values, two flavours sharing the same two add sites:
+//   plain    : sum_l v_l
+//   weighted : sum_l l * v_l = sum_l (sum_{m > l} v_m): shift down one lane, inclusive Hillis-Steele suffix scan,
+//              then the plain butterfly sum of the scan.
+// Shuffles only -- no shared memory; every lane returns the total.
+template <class F> __device__ __forceinline__ Xyzz<F> warp_reduce(Xyzz<F> v, bool weighted) {
+    const int lane = threadIdx.x & 31;
+    if (weighted) {                                            // warp-uniform
+        Xyzz<F> o = shfl_xyzz(v, (lane + 1) & 31);
+        v = select(lane == 31, xyzz_infinity<F>(), o);
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            o = shfl_xyzz(v, (lane + d) & 31);
+            o = select(lane + d >= 32, xyzz_infinity<F>(), o);
+            v = xadd(v, o);
+        }
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        Xyzz<F> o = shfl_xyzz(v, lane ^ d);
+        v = xadd(v, o);
+    }
+    return v;
+}
+
+// one block of 8 warps per window; the tpw strips of the window form tpw/32 rows of 32.  Pass 0: each row is reduced by
+// one warp into P = sum S1, Q = sum l*S1, A = sum S2 (shared memory, 3 x nrows entries).  Pass 1: warp 0 reduces the
+// rows: wp = sum row*P_row, qs = sum Q_row, as = sum A_row.  Then W = as + strip * (32 * wp + qs).
+template <class F> __global__ void __launch_bounds__(256) k_msm_reduce2(const uint32_t *s1, const uint32_t *s2, MsmGeom g, uint32_t *wsum) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    __shared__ __align__(16) uint32_t sm[100 * 4 * W];     // [P | Q | A] rows, then [wp | qs | as] in slots 96..98
+    const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nrows = g.tpw >> 5;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        // items of this pass for this warp: pass 0 -> (row, kind) for rows wid, wid+8, ..; pass 1 -> kind only (warp 0)
+        const uint32_t nitems = pass == 0 ? 3 * ((nrows + 7 - wid) / 8) : (wid == 0 ? 3u : 0u);
+#pragma unroll 1
+        for (uint32_t it = 0; it < nitems; it++) {
+            const uint32_t kind = it % 3;                      // 0: P / wp (weighted in pass 1), 1: Q (weighted in pass 0) / qs, 2: A / as
+            Xyzz<F> v;
+            bool weighted;
+            uint32_t dst;
+            if (pass == 0) {
+                const uint32_t row = wid + 8 * (it / 3);
+                v = load_xyzz<F>(kind == 2 ? s2 : s1, (size_t)w * g.tpw + row * 32 + lane);
+                weighted = kind == 1;
+                dst = kind * 32 + row;
+            } else {
+                v = load_xyzz<F>(sm, kind * 32 + lane);
+                v = select(lane >= nrows, xyzz_infinity<F>(), v);
+                weighted = kind == 0;
+                dst = 96 + kind;
+            }
+            v = warp_reduce(v, weighted);
+            if (lane == 0) store_xyzz<F>(sm, dst, v);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Xyzz<F> b = load_xyzz<F>(sm, 96);                      // wp
+        uint32_t ls = 0;
+        while ((1u << ls) < g.strip) ls++;
+#pragma unroll 1
+        for (uint32_t i = 0; i <= 5 + ls; i++) {               // b = strip * (32 * wp + qs)
+            if (i == 5) b = xadd(b, load_xyzz<F>(sm, 97));
+            if (i < 5 + ls) b = xdbl(b);
+        }
+        store_xyzz<F>(wsum, w, xadd(load_xyzz<F>(sm, 98), b));
+    }
+}
+
+// Horner over the windows (most significant first); result as XYZZ (out_xyzz) and as affine wire words (out_wire)
+template <class F> __global__ void k_msm_final(const uint32_t *wsum, MsmGeom g, uint32_t *out_wire) {
+    if (threadIdx.x || blockIdx.x) return;
+    Xyzz<F> acc = load_xyzz<F>(wsum, g.nwin - 1);
+#pragma unroll 1
+    for (int w = (int)g.nwin - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (uint32_t j = 0; j < g.c; j++) acc = xdbl(acc);
+        acc = xadd(acc, load_xyzz<F>(wsum, w));
+    }
+    bool inf = is_zero(acc.zz);
+    F t = inv(mul(acc.zz, acc.zzz));
+    Aff<F> a;
+    a.x = mul(acc.x, mul(t, acc.zzz));        // X / ZZ
+    a.y = mul(acc.y, mul(t, acc.zz));         // Y / ZZZ
+    uint32_t o[Wire<F>::WORDS_UNCOMPRESSED];
+    point_encode<F>(o, a, inf, ENC_UNCOMPRESSED);
+    for (int j = 0; j < Wire<F>::WORDS_UNCOMPRESSED; j++) out_wire[j] = o[j];
+}
+
+// sum of `count` affine wire points (multi-GPU combination of per-rank results)
+template <class F> __global__ void k_sum_points(const uint32_t *wire, uint32_t count, uint32_t *out_wire, unsigned long long *err) {
+    if (threadIdx.x || blockIdx.x) return;
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
+    Xyzz<F> acc = xyzz_infinity<F>();
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t w[WU];
+        for (int j = 0; j < WU; j++) w[j] = wire[i * WU + j];
+        Aff<F> a;
+        bool inf;
+        int rc = point_decode<F>(a, inf, w, ENC_UNCOMPRESSED, true);
+        if (rc) { report_err(err, i, P2B_EDECODE, rc); continue; }
+        if (!inf) acc = xyzz_madd(acc, a);
+    }
+    bool inf = is_zero(acc.zz);
+    F t = inv(mul(acc.zz, acc.zzz));
+    Aff<F> a;
+    a.x = mul(acc.x, mul(t, acc.zzz));
+    a.y = mul(acc.y, mul(t, acc.zz));
+    uint32_t o[WU];
+    point_encode<F>(o, a, inf, ENC_UNCOMPRESSED);
+    for (int j = 0; j < WU; j++) out_wire[j] = o[j];
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+static inline MsmGeom msm_geometry(size_t n) {
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    MsmGeom g;
+    int c = (int)lg - 4;
+    if (c < 6) c = 6;
+    if (c > 16) c = 16;
+    g.c = (uint32_t)c;
+    g.nwin = 254 / g.c + 1;
+    g.nb = 1u << (g.c - 1);
+    g.nbk = g.nb + 1;
+    g.strip = g.nb > 1024 ? g.nb / 1024 : 1;
+    g.tpw = g.nb / g.strip;
+    return g;
+}
+
+template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire) {
+    constexpr int W = FieldTraits<F>::WORDS, WU = Wire<F>::WORDS_UNCOMPRESSED;
+    if (n >= ((size_t)1 << 31)) return ctx_fail(c, P2B_EARG, "msm: n must be < 2^31");
+    MsmGeom g = msm_geometry(n ? n : 1);
+    const size_t nslots = (size_t)g.nwin * g.nbk;
+    const size_t xy = (size_t)4 * W * 4;                       // bytes per XYZZ point
+    int rc;
+    // msm_a: affine Montgomery points ; msm_b: hist | offsets | cursor ; msm_c: sorted entries ; msm_d: buckets | s1 | s2 | wsum
+    if ((rc = dev_reserve(c, c->msm_a, (n ? n : 1) * WU * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_b, (3 * nslots + 4) * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * (n ? n : 1) * 4))) return rc;
+    const size_t nred = (size_t)g.nwin * g.tpw;
+    if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin) * xy))) return rc;
+    uint32_t *aff = (uint32_t *)c->msm_a.p;
+    uint32_t *hist = (uint32_t *)c->msm_b.p, *offsets = hist + nslots, *cursor = offsets + nslots + 1;
+    uint32_t *sorted = (uint32_t *)c->msm_c.p;
+    uint32_t *buckets = (uint32_t *)c->msm_d.p, *s1 = buckets + nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
+    P2B_CUDA(c, cudaMemsetAsync(hist, 0, nslots * 4, c->stream));
+    int grid = (int)((n + 255) / 256);
+    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+    if (grid < 1) grid = 1;
+    k_msm_prepare<F><<<grid, 256, 0, c->stream>>>((const uint32_t *)d_points, aff, n, c->d_err);
+    k_msm_hist<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err);
+    k_msm_scan<<<1, 1024, 0, c->stream>>>(hist, offsets, cursor, (uint32_t)nslots);
+    k_msm_scatter<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, cursor, sorted);
+    int agrid = (int)((nslots + 127) / 128);
+    k_msm_accumulate<F><<<agrid, 128, 0, c->stream>>>(aff, offsets, sorted, g, buckets);
+    k_msm_reduce1<F><<<(int)((nred + 127) / 128), 128, 0, c->stream>>>(buckets, g, s1, s2);
+    k_msm_reduce2<F><<<g.nwin, 256, 0, c->stream>>>(s1, s2, g, wsum);
+    k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
+    c->launches += 8;
+    P2B_CUDA(c, cudaGetLastError());
+    return P2B_OK;
+}
+
+
+}  // namespace p2b

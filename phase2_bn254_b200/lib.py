@@ -24,8 +24,8 @@ SYMBOLS = [
     "p2b_g2_batch_mul_powers", "p2b_g1_batch_mul_dev", "p2b_g2_batch_mul_dev",
     "p2b_g1_batch_mul_powers_dev", "p2b_g2_batch_mul_powers_dev", "p2b_sync",
     "p2b_pot_accumulator_size", "p2b_pot_transform", "p2b_phase2_transcript", "p2b_phase2_contribute",
-    "p2b_g1_msm", "p2b_g2_msm", "p2b_g1_msm_dev", "p2b_g2_msm_dev", "p2b_g1_msm_partial_dev",
-    "p2b_g2_msm_partial_dev", "p2b_g1_sum_partials", "p2b_g2_sum_partials", "p2b_fr_fft", "p2b_fr_fft_dev",
+    "p2b_g1_msm", "p2b_g2_msm", "p2b_g1_msm_dev", "p2b_g2_msm_dev", "p2b_g1_sum_points", "p2b_g2_sum_points",
+    "p2b_fr_fft", "p2b_fr_fft_dev",
 ]
 
 
@@ -71,8 +71,7 @@ def load():
         if hasattr(lib, "p2b_%s_msm" % g):
             getattr(lib, "p2b_%s_msm" % g).argtypes = [vp, u8p, u8p, sz, u8p]
             getattr(lib, "p2b_%s_msm_dev" % g).argtypes = [vp, vp, vp, sz, u8p]
-            getattr(lib, "p2b_%s_msm_partial_dev" % g).argtypes = [vp, vp, vp, sz, u8p]
-            getattr(lib, "p2b_%s_sum_partials" % g).argtypes = [vp, u8p, sz, u8p]
+            getattr(lib, "p2b_%s_sum_points" % g).argtypes = [vp, u8p, sz, u8p]
     lib.p2b_sync.argtypes = [vp]
     lib.p2b_pot_accumulator_size.argtypes = [u32, i32]
     lib.p2b_pot_accumulator_size.restype = u64
@@ -225,17 +224,12 @@ class Context:
         self._check(fn(self.h, _ptr(d_points), _ptr(d_scalars), n, _ptr(out)))
         return out.tobytes()
 
-    def msm_partial_dev(self, group, d_points, d_scalars, n):
-        out = np.empty(192 if group == G2 else 96, dtype=np.uint8)
-        fn = self.lib.p2b_g2_msm_partial_dev if group == G2 else self.lib.p2b_g1_msm_partial_dev
-        self._check(fn(self.h, _ptr(d_points), _ptr(d_scalars), n, _ptr(out)))
-        return out
-
-    def sum_partials(self, group, partials):
-        p = _host(partials)
-        count = p.size // (192 if group == G2 else 96)
+    def sum_points(self, group, points):
+        """Sum of uncompressed points (combines the per-rank MSM results after the all-gather)."""
+        p = _host(points)
+        count = p.size // enc_size(group, ENC_UNCOMPRESSED)
         out = np.empty(enc_size(group, ENC_UNCOMPRESSED), dtype=np.uint8)
-        fn = self.lib.p2b_g2_sum_partials if group == G2 else self.lib.p2b_g1_sum_partials
+        fn = self.lib.p2b_g2_sum_points if group == G2 else self.lib.p2b_g1_sum_points
         self._check(fn(self.h, _ptr(p), count, _ptr(out)))
         return out.tobytes()
 

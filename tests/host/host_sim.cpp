@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../phase2_bn254_b200/csrc/codec.cuh"
 #include "../../phase2_bn254_b200/csrc/smul.cuh"
+#include "../../phase2_bn254_b200/csrc/xyzz.cuh"
 using namespace p2b;
 
 static void be_to_words(const uint8_t *b, uint32_t *w, int nwords) { memcpy(w, b, nwords * 4); }
@@ -100,5 +101,30 @@ void sim_field(int field, int op, const uint8_t *a_be, const uint8_t *b_be, uint
         limbs_to_be_words(from_mont(r), wo);
     }
     memcpy(out_be, wo, 32);
+}
+
+// XYZZ check: sum_i k_i P_i by plain double-and-add in XYZZ coordinates (exercises xyzz_madd / xyzz_add / xyzz_dbl)
+int sim_xyzz_msm(const uint8_t *points, const uint8_t *scalars_be, int n, uint8_t *out) {
+    Xyzz<Fq> total = xyzz_infinity<Fq>();
+    for (int i = 0; i < n; i++) {
+        uint32_t w[16]; be_to_words(points + 64 * i, w, 16);
+        Aff<Fq> p; bool inf;
+        if (point_decode<Fq>(p, inf, w, ENC_UNCOMPRESSED, true)) return 1;
+        uint32_t k[8]; k_from_be(scalars_be + 32 * i, k);
+        Xyzz<Fq> acc = xyzz_infinity<Fq>();
+        for (int b = 255; b >= 0; b--) {
+            acc = xyzz_dbl(acc);
+            if (!inf && ((k[b >> 5] >> (b & 31)) & 1)) acc = xyzz_madd(acc, p);
+        }
+        total = xyzz_add(total, acc);
+    }
+    bool inf = is_zero(total.zz);
+    Fq t = inv(mul(total.zz, total.zzz));
+    Aff<Fq> a;
+    a.x = mul(total.x, mul(t, total.zzz));
+    a.y = mul(total.y, mul(t, total.zz));
+    uint32_t ow[16]; point_encode<Fq>(ow, a, inf, ENC_UNCOMPRESSED);
+    words_to_be(ow, out, 16);
+    return 0;
 }
 }
