@@ -1,0 +1,319 @@
+// fft.cu -- K6: radix-2 FFT / iFFT (and the coset variants) over the BN254 scalar field Fr on sm_100a.
+//
+// GPU replacement for bellman's EvaluationDomain::{fft, ifft, coset_fft, icoset_fft} over Scalar<E>
+// (bellman/src/domain.rs:154-205) and the best_fft / serial_fft / parallel_fft kernels under them
+// (domain.rs:263-376).  Natural order in, natural order out, in place from the caller's point of view;
+// every output is the canonical residue of a uniquely defined field element, so the schedule is free.
+//
+// Schedule: Stockham autosort, ceil(log n / 8) passes over HBM, each pass a radix-2^r (r <= 8) step done in
+// shared memory:
+//   pass with Ns = product of the earlier radices, for column j in [0, n / R):
+//       v[t]  = in[j + t * n/R] * w^(t * (j mod Ns)),  w = omega_(Ns*R)            (twiddle at load)
+//       V     = DFT_R(v)                                                           (r DIF stages in smem)
+//       out[(j div Ns) * Ns * R + (j mod Ns) + q * Ns] = V[q]                      (autosort scatter)
+// A block owns a tile of J = 2048 / R consecutive columns so that every global access is a run of J (first
+// pass: R) consecutive 32-byte elements.  The first pass decodes the wire form (big-endian canonical -> Montgomery),
+// the last pass encodes it again and folds in the 1/n of the inverse transform, so the data makes exactly
+// `passes` round trips through HBM.  Algorithmic traffic: 64 B per element; actual: 64 B x passes.
+// Twiddles: w^e for e < n comes from a two-level table (2^ceil(log n / 2) + 2^floor(log n / 2) entries, L2
+// resident); the in-tile twiddles omega_256^t sit in shared memory.
+#include <cstdio>
+#include <cstring>
+#include "fp.cuh"
+#include "p2b_internal.h"
+
+namespace p2b {
+
+static constexpr int FFT_BLOCK = 256;
+static constexpr int FFT_TILE_LOG = 11;   // elements per tile (64 KB of shared memory + padding)
+static constexpr int FFT_RMAX = 8;        // stages per pass
+
+struct FftPass {
+    const uint32_t *in;
+    uint32_t *out;
+    uint32_t log_n, r, log_ns, log_te;    // tile has 2^log_te elements = 2^(log_te - r) columns x 2^r
+    uint32_t lb;                          // bits of the low twiddle table
+    const Fr *tlo, *thi, *twr;
+    uint32_t scale[8];                    // LAST: raw multiplier (1 or n^-1, canonical limbs)
+    unsigned long long *err;
+};
+
+__device__ __forceinline__ uint32_t fft_phys(uint32_t slot) { return slot + (slot >> 5); }
+
+template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK) k_fft_pass(FftPass p) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const uint32_t te = 1u << p.log_te, plane = te + (te >> 5) + 1;
+    uint32_t *u = sm;                      // 8 planes of `plane` words
+    uint32_t *tw = sm + 8 * plane;         // 8 planes of 128 words: omega_256^t
+    const uint32_t tid = threadIdx.x, r = p.r, R = 1u << r, log_j = p.log_te - r, J = 1u << log_j;
+    for (uint32_t i = tid; i < 128 * 8; i += FFT_BLOCK) tw[(i & 7) * 128 + (i >> 3)] = p.twr[i >> 3].l[i & 7];
+    const size_t jbase = (size_t)blockIdx.x << log_j;
+    const uint32_t ns_mask = (1u << p.log_ns) - 1u;
+    // ---- load (+ decode / twiddle) ----
+    for (uint32_t e = tid; e < te; e += FFT_BLOCK) {
+        const uint32_t jj = e & (J - 1), t = e >> log_j;
+        const size_t j = jbase + jj, idx = j + ((size_t)t << (p.log_n - r));
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.in + idx * 8);
+        uint4 a = __ldg(src), b = __ldg(src + 1);
+        Fr v;
+        if (FIRST) {
+            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            v = limbs_from_be_words<FrP>(w);
+            if (!is_canonical(v)) atomicMin(p.err, (unsigned long long)(((uint64_t)idx << 8) | (P2B_EARG << 4)));
+            v = to_mont(v);
+        } else {
+            v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+            if (p.log_ns) {
+                const uint32_t k = (uint32_t)j & ns_mask;
+                const uint32_t ex = (t * k) << (p.log_n - p.log_ns - r);
+                Fr w = mul(p.tlo[ex & ((1u << p.lb) - 1u)], p.thi[ex >> p.lb]);
+                v = mul(v, w);
+            }
+        }
+        const uint32_t ph = fft_phys(t * J + jj);
+#pragma unroll
+        for (int w = 0; w < 8; w++) u[w * plane + ph] = v.l[w];
+    }
+    __syncthreads();
+    // ---- r decimation-in-frequency stages: u[bitrev(q)] = V[q] ----
+    for (uint32_t s = 0; s < r; s++) {
+        const uint32_t lh = r - 1 - s, half = 1u << lh;
+        for (uint32_t bi = tid; bi < (te >> 1); bi += FFT_BLOCK) {
+            const uint32_t jj = bi & (J - 1), b = bi >> log_j;
+            const uint32_t pos = b & (half - 1), i0 = ((b >> lh) << (lh + 1)) + pos, i1 = i0 + half;
+            const uint32_t p0 = fft_phys(i0 * J + jj), p1 = fft_phys(i1 * J + jj);
+            Fr x, y;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { x.l[w] = u[w * plane + p0]; y.l[w] = u[w * plane + p1]; }
+            Fr sum = add(x, y), d = sub(x, y);
+            if (half > 1) {
+                const uint32_t ti = (pos << s) << (FFT_RMAX - r);
+                Fr wv;
+#pragma unroll
+                for (int w = 0; w < 8; w++) wv.l[w] = tw[w * 128 + ti];
+                d = mul(d, wv);
+            }
+#pragma unroll
+            for (int w = 0; w < 8; w++) { u[w * plane + p0] = sum.l[w]; u[w * plane + p1] = d.l[w]; }
+        }
+        __syncthreads();
+    }
+    // ---- autosort scatter (+ encode) ----
+    Fr scale;
+#pragma unroll
+    for (int w = 0; w < 8; w++) scale.l[w] = p.scale[w];
+    for (uint32_t e = tid; e < te; e += FFT_BLOCK) {
+        uint32_t jj, q;
+        if (p.log_ns == 0) { q = e & (R - 1); jj = e >> r; }          // first pass: runs of R consecutive outputs
+        else { jj = e & (J - 1); q = e >> log_j; }                    // later passes: runs of J consecutive outputs
+        const uint32_t qr = r ? (__brev(q) >> (32 - r)) : 0u;
+        const uint32_t ph = fft_phys(qr * J + jj);
+        Fr v;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v.l[w] = u[w * plane + ph];
+        const size_t j = jbase + jj, k = j & ns_mask;
+        const size_t idx = (((j >> p.log_ns) << (p.log_ns + r)) | k) + ((size_t)q << p.log_ns);
+        uint32_t o[8];
+        if (LAST) {
+            v = mul(v, scale);                                        // Montgomery -> canonical (x n^-1)
+            limbs_to_be_words(v, o);
+        } else {
+#pragma unroll
+            for (int w = 0; w < 8; w++) o[w] = v.l[w];
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(p.out + idx * 8);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// tables: tlo[i] = base^i (i < 2^lb), thi[i] = base^(i << lb) (i < 2^hb), optional twr[i] = root256^i (i < 128).
+// hi_raw: store thi as canonical limbs instead of Montgomery (so that mont_mul(tlo, thi) is canonical).
+static __global__ void k_fft_tables(Fr *tlo, Fr *thi, Fr *twr, Fr base, Fr root256, uint32_t lb, uint32_t hb, int hi_raw) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, nlo = 1u << lb, nhi = 1u << hb;
+    if (i < nlo) tlo[i] = pow_u64(base, i);
+    else if (i < nlo + nhi) {
+        Fr v = pow_u64(base, (uint64_t)(i - nlo) << lb);
+        thi[i - nlo] = hi_raw ? from_mont(v) : v;
+    } else if (twr && i < nlo + nhi + 128) twr[i - nlo - nhi] = pow_u64(root256, i - nlo - nhi);
+}
+
+// data[i] <- data[i] * g^i on the wire form (distribute_powers, domain.rs:176-189)
+static __global__ void __launch_bounds__(256) k_fr_distribute_powers(uint32_t *data, size_t n, const Fr *glo, const Fr *ghi_raw,
+                                                                      uint32_t lb, unsigned long long *err) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 *ptr = reinterpret_cast<uint4 *>(data + i * 8);
+        uint4 a = ptr[0], b = ptr[1];
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        Fr v = limbs_from_be_words<FrP>(w);
+        if (!is_canonical(v)) atomicMin(err, (unsigned long long)(((uint64_t)i << 8) | (P2B_EARG << 4)));
+        Fr s = mul(glo[i & ((1u << lb) - 1u)], ghi_raw[i >> lb]);     // canonical g^i
+        v = mul(to_mont(v), s);                                       // canonical v * g^i
+        limbs_to_be_words(v, w);
+        ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+static Fr host_fr_from_u64(uint64_t v) {
+    Fr a = fp_zero<FrP>();
+    a.l[0] = (uint32_t)v; a.l[1] = (uint32_t)(v >> 32);
+    return to_mont(a);
+}
+// 2^28-th root of unity 7^((r-1)/2^28) (fr.rs:3-6 PrimeFieldGenerator = 7, S = 28), Montgomery form
+static Fr host_root_of_unity() {
+    uint32_t e[8];
+    for (int i = 0; i < 8; i++) e[i] = FrP::p(i);
+    e[0] -= 1;                                           // r - 1 (no borrow: r is odd)
+    for (int i = 0; i < 8; i++) {                        // >> 28
+        uint64_t lo = e[i], hi = i + 1 < 8 ? e[i + 1] : 0;
+        e[i] = (uint32_t)(((hi << 32) | lo) >> 28);
+    }
+    return pow_limbs(host_fr_from_u64(7), e);
+}
+
+struct FftPlan {
+    uint32_t npass, r[4], log_te;
+};
+static FftPlan fft_plan(uint32_t log_n) {
+    FftPlan pl;
+    pl.npass = log_n ? (log_n + FFT_RMAX - 1) / FFT_RMAX : 1;
+    uint32_t left = log_n;
+    for (uint32_t i = 0; i < pl.npass; i++) {
+        pl.r[i] = (left + (pl.npass - i) - 1) / (pl.npass - i);
+        left -= pl.r[i];
+    }
+    pl.log_te = log_n < (uint32_t)FFT_TILE_LOG ? log_n : FFT_TILE_LOG;
+    return pl;
+}
+
+static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
+    if (c->fft_tw.p && c->fft_tw_log_n == log_n && c->fft_tw_inverse == inverse) return P2B_OK;
+    const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
+    const size_t nent = ((size_t)1 << lb) + ((size_t)1 << hb) + 128;
+    int rc = dev_reserve(c, c->fft_tw, 2 * nent * sizeof(Fr));      // [omega tables | coset tables]
+    if (rc) return rc;
+    Fr root = host_root_of_unity(), omega = root, root256 = root;
+    for (uint32_t i = log_n; i < 28; i++) omega = sqr(omega);
+    for (uint32_t i = FFT_RMAX; i < 28; i++) root256 = sqr(root256);
+    Fr g = host_fr_from_u64(7);
+    if (inverse) { omega = inv(omega); root256 = inv(root256); g = inv(g); }
+    Fr *tlo = (Fr *)c->fft_tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
+    Fr *glo = twr + 128, *ghi = glo + ((size_t)1 << lb);
+    const uint32_t threads = (uint32_t)nent;
+    k_fft_tables<<<(threads + 127) / 128, 128, 0, c->stream>>>(tlo, thi, twr, omega, root256, lb, hb, 0);
+    k_fft_tables<<<(threads + 127) / 128, 128, 0, c->stream>>>(glo, ghi, nullptr, g, g, lb, hb, 1);
+    c->launches += 2;
+    P2B_CUDA(c, cudaGetLastError());
+    c->fft_tw_log_n = log_n;
+    c->fft_tw_inverse = inverse;
+    return P2B_OK;
+}
+
+template <bool FIRST, bool LAST> static int fft_launch_pass(Ctx *c, const FftPass &p, uint32_t blocks, size_t smem) {
+    static bool attr = false;
+    if (!attr) {
+        P2B_CUDA(c, cudaFuncSetAttribute(k_fft_pass<FIRST, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        attr = true;
+    }
+    k_fft_pass<FIRST, LAST><<<blocks, FFT_BLOCK, smem, c->stream>>>(p);
+    c->launches++;
+    return P2B_OK;
+}
+
+// d_data: 2^log_n wire scalars; d_tmp: scratch of the same size.  The result lands in *d_result (d_data or d_tmp).
+static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int inverse, int coset, void **d_result) {
+    if (log_n > 28) return ctx_fail(c, P2B_EARG, "fft: log_n must be <= 28 (Fr::S, domain.rs:64-78)");
+    int rc = fft_tables(c, log_n, inverse);
+    if (rc) return rc;
+    const size_t n = (size_t)1 << log_n;
+    const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
+    Fr *tlo = (Fr *)c->fft_tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
+    Fr *glo = twr + 128, *ghi = glo + ((size_t)1 << lb);
+    int sgrid = (int)((n + 255) / 256);
+    if (sgrid > c->sm_count * 8) sgrid = c->sm_count * 8;
+    if (coset && !inverse) {   // coset_fft: distribute_powers(g) then fft (domain.rs:191-195)
+        k_fr_distribute_powers<<<sgrid, 256, 0, c->stream>>>((uint32_t *)d_data, n, glo, ghi, lb, c->d_err);
+        c->launches++;
+    }
+    FftPlan pl = fft_plan(log_n);
+    FftPass p;
+    memset(&p, 0, sizeof p);
+    p.log_n = log_n; p.log_te = pl.log_te; p.lb = lb; p.tlo = tlo; p.thi = thi; p.twr = twr; p.err = c->d_err;
+    Fr scale = fp_zero<FrP>();
+    scale.l[0] = 1;
+    if (inverse) scale = from_mont(inv(host_fr_from_u64((uint64_t)n)));    // canonical n^-1 (domain.rs:163-173)
+    memcpy(p.scale, scale.l, 32);
+    const uint32_t te = 1u << pl.log_te;
+    const size_t smem = (size_t)(8 * (te + (te >> 5) + 1) + 8 * 128) * 4;
+    const uint32_t blocks = (uint32_t)(n >> pl.log_te);
+    void *src = d_data, *dst = d_tmp;
+    uint32_t log_ns = 0;
+    for (uint32_t i = 0; i < pl.npass; i++) {
+        p.in = (const uint32_t *)src; p.out = (uint32_t *)dst; p.r = pl.r[i]; p.log_ns = log_ns;
+        const bool first = i == 0, last = i + 1 == pl.npass;
+        if (first && last) rc = fft_launch_pass<true, true>(c, p, blocks, smem);
+        else if (first) rc = fft_launch_pass<true, false>(c, p, blocks, smem);
+        else if (last) rc = fft_launch_pass<false, true>(c, p, blocks, smem);
+        else rc = fft_launch_pass<false, false>(c, p, blocks, smem);
+        if (rc) return rc;
+        log_ns += pl.r[i];
+        void *t = src; src = dst; dst = t;
+    }
+    if (coset && inverse) {    // icoset_fft: ifft then distribute_powers(g^-1) (domain.rs:197-205)
+        k_fr_distribute_powers<<<sgrid, 256, 0, c->stream>>>((uint32_t *)src, n, glo, ghi, lb, c->d_err);
+        c->launches++;
+    }
+    P2B_CUDA(c, cudaGetLastError());
+    *d_result = src;
+    return P2B_OK;
+}
+
+int launch_fr_fft(Ctx *c, void *d_data, uint32_t log_n, int inverse, int coset) {
+    const size_t bytes = (size_t)32 << log_n;
+    int rc = dev_reserve(c, c->misc, bytes);
+    if (rc) return rc;
+    void *res = nullptr;
+    if ((rc = fft_run(c, d_data, c->misc.p, log_n, inverse, coset, &res))) return rc;
+    if (res != d_data) P2B_CUDA(c, cudaMemcpyAsync(d_data, res, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return P2B_OK;
+}
+
+static int fft_begin(Ctx *c) {
+    P2B_CUDA(c, cudaSetDevice(c->device));
+    c->last_error.clear();
+    P2B_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream));
+    return P2B_OK;
+}
+static int fft_host(Ctx *c, uint8_t *data, uint32_t log_n, int inverse, int coset) {
+    if (!data) return ctx_fail(c, P2B_EARG, "null buffer");
+    if (log_n > 28) return ctx_fail(c, P2B_EARG, "fft: log_n must be <= 28 (Fr::S, domain.rs:64-78)");
+    int rc = fft_begin(c);
+    if (rc) return rc;
+    const size_t bytes = (size_t)32 << log_n;
+    if ((rc = dev_reserve(c, c->stage_in[0], bytes))) return rc;
+    if ((rc = dev_reserve(c, c->misc, bytes))) return rc;
+    P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[0].p, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    void *res = nullptr;
+    if ((rc = fft_run(c, c->stage_in[0].p, c->misc.p, log_n, inverse, coset, &res))) return rc;
+    P2B_CUDA(c, cudaMemcpyAsync(data, res, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return ctx_collect_error(c);
+}
+static int fft_dev(Ctx *c, void *d_data, uint32_t log_n, int inverse, int coset) {
+    if (!d_data) return ctx_fail(c, P2B_EARG, "null buffer");
+    P2B_CUDA(c, cudaSetDevice(c->device));
+    return launch_fr_fft(c, d_data, log_n, inverse, coset);
+}
+
+}  // namespace p2b
+
+using namespace p2b;
+extern "C" {
+int p2b_fr_fft(p2b_ctx *h, uint8_t *data, uint32_t log_n, int inverse, int coset) {
+    return h ? fft_host(&h->c, data, log_n, inverse, coset) : P2B_EARG;
+}
+int p2b_fr_fft_dev(p2b_ctx *h, void *d_data, uint32_t log_n, int inverse, int coset) {
+    return h ? fft_dev(&h->c, d_data, log_n, inverse, coset) : P2B_EARG;
+}
+}

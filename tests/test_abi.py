@@ -1,0 +1,68 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/p2b.h declares, the ctypes binding covers
+them all, and the product path fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "p2b.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(p2b_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_binding_and_exports_agree():
+    from phase2_bn254_b200 import lib
+    hdr = header_symbols()
+    assert hdr == sorted(lib.SYMBOLS)
+    so = lib.load()
+    for name in hdr:
+        assert hasattr(so, name), name
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", lib.LIB_PATH]).decode()
+    exported = sorted(set(re.findall(r" T (p2b_[a-z0-9_]+)", nm)))
+    assert exported == hdr, "exported symbols differ from include/p2b.h"
+    assert b"sm_100a" in so.p2b_version()
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "p2b.h")).read()
+    assert "torch" not in src and "at::" not in src and "#include <cuda" not in src
+
+
+def test_library_is_built_for_sm_100a():
+    from phase2_bn254_b200 import lib
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from phase2_bn254_b200 import lib
+    with pytest.raises(lib.P2BError) as e:
+        lib.Context(0)
+    assert e.value.code == lib.ECUDA
+    so = lib.load()
+    so.p2b_g1_msm.restype = ctypes.c_int
+    assert so.p2b_g1_msm(None, None, None, 0, None) == lib.EARG           # null ctx is an argument error, not a crash
+
+
+def test_geometry_matches_reference_table():
+    """powersoftau/src/parameters.rs:72-107 at the configs of SURVEY.md section 8."""
+    from phase2_bn254_b200 import lib
+    from phase2_bn254_b200.powersoftau import CeremonyParams
+    so = lib.load()
+    for size, acc, contrib in ((10, 393344, 197472), (20, 402653312, 201327456), (26, 25769803904, 12884902752),
+                               (28, 103079215232, 51539608416)):
+        p = CeremonyParams(size, 256)
+        assert p.accumulator_size == acc and p.contribution_size == contrib
+        assert so.p2b_pot_accumulator_size(size, 0) == acc
+        assert so.p2b_pot_accumulator_size(size, 1) == contrib - 768
