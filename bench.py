@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the phase2-bn254 B200 compute core.
+
+Metric (BASELINE.json): BN254 G1 Pippenger MSM throughput in Mscalar-mul/s at 2^26 terms per GPU
+(`bellman/src/multiexp.rs:330-475`), plus -- as extra keys on the same JSON line -- the
+phase-2 `contribute` wall time at 2^20 constraints (config 3), batch_exp throughput (the transform hot loop) and the
+Fr FFT at 2^24 (config 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n L] [--impl ours|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one MSM over the rank's 2^L synthetic (point, scalar) pairs.  `value` is timed with the inputs already in
+HBM (CUDA events on the library's stream + barrier/synchronize on both sides, max over ranks); `e2e` is the same call
+through the host-buffer C ABI entry point (`p2b_g1_msm`: pinned host buffers, H2D of 96 B/term and D2H of the 64-byte
+result inside the timed region).  N > 1: weak scaling, every rank owns 2^L terms, the per-rank results are all-gathered
+over NCCL and summed on every rank (phase2_bn254_b200/dist.py).  `--impl reference` times the CPU restatement of the
+reference algorithm (oracle/, the reference itself is Rust and cannot be built here) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+G1_GEN = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")
+G2_GEN = b"".join(v.to_bytes(32, "big") for v in (
+    11559732032986387107991004021392285783925812861821192530917403151452391805634,
+    10857046999023057135944570762232829481370756359578518086990519993285655852781,
+    4082367875863433681332203403145435568316851327593401208105741076214120093531,
+    8495653923123431417604973247489272438418190587263600148770280649306958101930))
+METRIC = "BN254 G1 MSM throughput"
+UNIT = "Mscalar-mul/s"
+TAU = 0x1d7a3f6c2b9e80415f6a7b8c9d0e1f2031425364758697a8b9cadbecfd0e1f21 % R_MOD
+
+
+def be(v):
+    return int(v).to_bytes(32, "big")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs (oracle)
+def cpu_points_scalars(n, seed=1):
+    """n G1 points tau^(i+1) G and n scalars, generated on the CPU with the oracle (bounded sample sizes only)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as oc
+    pts = oc.batch_mul_powers(0, G1_GEN * n, be(TAU), None, 1, threads=host_cores())
+    rng = np.random.default_rng(seed)
+    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 0] &= 0x1f
+    return pts, sc.tobytes()
+
+
+def cpu_msm_rate(log_sample, steps=1, warmup=0):
+    """(Mscalar-mul/s, seconds per MSM, cores) of the oracle's Pippenger (bellman's algorithm) on 2^log_sample terms."""
+    n = 1 << log_sample
+    pts, sc = cpu_points_scalars(n)
+    import oracle as oc
+    cores = host_cores()
+    for _ in range(warmup):
+        oc.msm(0, pts, sc, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oc.msm(0, pts, sc, threads=cores)
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt / 1e6, dt, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    log_sample = args.ref_log_n
+    rate, dt, cores = cpu_msm_rate(log_sample, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "g1_msm_2^%d" % args.log_n, "terms_per_gpu": 1 << args.log_n},
+        "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "one Pippenger MSM over 2^%d of the workload's terms per step (bellman window rule "
+                                   "c=ceil(ln n), one task per window and chunk on all host threads); the reference is Rust "
+                                   "and cannot be built here, this is oracle/p2b_oracle.c" % log_sample},
+        "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        self.mark = 0
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        rows = [s for t, s in self.samples if t0 <= t <= t1] or [s for _, s in self.samples[-3:]]
+        sm, mx, reasons = [], 0, set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ----------------------------------------------------------------------------------------------- GPU workload
+def make_scalars(torch, n, seed, device):
+    """n x 32 BE bytes: uniform 254-bit values folded into [0, r) (values >= r get their top nibble cleared)."""
+    rbytes = torch.tensor(list(be(R_MOD)), dtype=torch.int16, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, 32), dtype=torch.uint8, device=device)
+    step = 1 << 22
+    for lo in range(0, n, step):
+        m = min(step, n - lo)
+        s = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=device, generator=g)
+        s[:, 0] &= 0x3f
+        d = s.to(torch.int16) - rbytes
+        nz = d != 0
+        first = nz.to(torch.uint8).argmax(dim=1, keepdim=True)
+        ge = (d.gather(1, first).squeeze(1) > 0) | (~nz.any(dim=1))
+        s[ge, 0] &= 0x0f
+        out[lo:lo + m] = s
+    return out.reshape(-1)
+
+
+def make_points(torch, np, ctx, group, n, start, device):
+    """n points tau^(start+i) * G generated on the GPU by the library's own batch_exp (a valid powers-of-tau vector)."""
+    gen = G2_GEN if group else G1_GEN
+    src = torch.from_numpy(np.frombuffer(gen, dtype=np.uint8).copy()).to(device).repeat(n)
+    pts = torch.empty(n * len(gen), dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+    ctx.batch_mul_powers_dev(group, src.data_ptr(), pts.data_ptr(), n, np.frombuffer(be(TAU), dtype=np.uint8), None, start)
+    ctx.sync()
+    del src
+    return pts
+
+
+def timed(torch, stream, fn, reps):
+    """fn() `reps` times between two CUDA events on the library's stream; returns (device ms, wall ms) per rep."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3 / reps
+    return e0.elapsed_time(e1) / reps, wall
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from phase2_bn254_b200 import dist as pdist
+    from phase2_bn254_b200 import lib
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = lib.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+    n = 1 << args.log_n
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    # ---- synthetic inputs, generated on the device: rank r owns terms [r n, (r+1) n)
+    pts = make_points(torch, np, ctx, 0, n, 1 + rank * n, device)
+    sc = make_scalars(torch, n, 0x8d313d76 + rank, device)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    result = {}
+
+    def step_dev():
+        if world > 1:
+            result["r"] = pdist.sharded_msm(ctx, 0, pts.data_ptr(), sc.data_ptr(), n, device=device, on_device=True)
+        else:
+            result["r"] = ctx.msm_dev(0, pts.data_ptr(), sc.data_ptr(), n)
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.profile(True)
+    launches0 = ctx.launch_count
+    barrier()
+    t_w0 = time.perf_counter()
+    dev_ms, wall_ms = timed(torch, stream, step_dev, args.steps)
+    barrier()
+    t_w1 = time.perf_counter()
+    launches = ctx.launch_count - launches0
+    prof = {name: ctx.profile_read(slot) for name, slot in (("sort", lib.PROF_MSM_SORT), ("accumulate", lib.PROF_MSM_ACCUMULATE),
+                                                            ("reduce", lib.PROF_MSM_REDUCE))}
+    ctx.profile(False)
+    # a multi-rank step also has NCCL work on another stream: the wall clock between the barriers is the step time there
+    step_ms = wall_ms if world > 1 else dev_ms
+    if world > 1:
+        t = torch.tensor([step_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    value = world * n / (step_ms * 1e-3) / 1e6
+
+    # ---- end to end: host (pinned) buffers through the host entry point, H2D + D2H inside the timed region
+    h_pts = torch.empty(pts.numel(), dtype=torch.uint8, pin_memory=True)
+    h_sc = torch.empty(sc.numel(), dtype=torch.uint8, pin_memory=True)
+    h_pts.copy_(pts); h_sc.copy_(sc)
+    torch.cuda.synchronize()
+    np_pts, np_sc = h_pts.numpy(), h_sc.numpy()
+
+    def step_host():
+        if world > 1:
+            result["e"] = pdist.sharded_msm(ctx, 0, np_pts, np_sc, n, device=device)
+        else:
+            result["e"] = ctx.msm(0, np_pts, np_sc)
+
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    _, e2e_ms = timed(torch, stream, step_host, args.steps)
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
+    assert result["e"] == result["r"], "host-buffer and device-buffer MSM disagree"
+    del h_pts, h_sc, np_pts, np_sc
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    acc_ms, acc_k = prof["accumulate"]
+    acc_avg_ms = acc_ms / max(1, acc_k)
+    achieved = 96.0 * n / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_msm_accumulate<Fq>@2^%d" % args.log_n)
+    except (OSError, ValueError):
+        pass
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "g1_msm_2^%d" % args.log_n, "terms_per_gpu": n, "points": "tau^i*G (uncompressed wire, 64 B)",
+                   "scalars": "uniform mod r (32 B BE)", "arithmetic": "8 x u32 limbs, 256-bit Montgomery, integer only", "l2": "inputs (%.1f GB) exceed L2" % (96.0 * n / 1e9),
+                   "parallelism": "point-range shards + all-gather of per-rank results" if world > 1 else "single GPU"},
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 96 * n, "d2h_bytes_per_step": 64,
+                "ms_per_step": round(e2e_ms, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.window(t_w0, t_w1),
+        "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fq>", "achieved": round(achieved, 2) if achieved else None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 5) if achieved else None,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 96 * n,
+                     "kernel_ms": round(acc_avg_ms, 4),
+                     "note": "integer-ALU bound (IMAD), not HBM bound: see DESIGN.md; share of step = %.2f" %
+                             (acc_avg_ms / dev_ms if dev_ms else 0)},
+        "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
+        "result_x": result["r"][:32].hex(),
+    }
+    clocks.stop()
+
+    if world == 1:
+        if not args.no_extras:
+            line["extras"] = extras(args, torch, np, ctx, stream, device, lib, pts, sc)
+        del pts, sc
+        torch.cuda.empty_cache()
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            rate, dt, cores = cpu_msm_rate(args.ref_log_n)
+            line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "one Pippenger MSM over 2^%d of the workload's terms (%.1f s), oracle/p2b_oracle.c "
+                                              "= C restatement of bellman multiexp on all host threads" % (args.ref_log_n, dt)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
+    """The other single-GPU configs of BASELINE.json, each timed a few times after the headline run."""
+    out = {}
+    nb = be(0x2b5d1c3e7f9a0b4c6d8e0f1a2b3c4d5e6f708192a3b4c5d6e7f8091a2b3c4d5e % R_MOD)
+    k = np.frombuffer(nb, dtype=np.uint8)
+    # -- config 2: G1 MSM at 2^20 (device resident)
+    m = 1 << 20
+    t, _ = timed(torch, stream, lambda: ctx.msm_dev(0, pts.data_ptr(), sc.data_ptr(), m), 5)
+    out["g1_msm_2^20"] = {"ms": round(t, 3), "Mscalar_mul_per_s": round(m / t / 1e3, 2)}
+    # -- batch_exp (the transform / contribute hot loop), device resident, 2^22 G1 and 2^20 G2
+    m = min(1 << 22, pts.numel() // 64)
+    outb = torch.empty(m * 64, dtype=torch.uint8, device=device)
+    ctx.profile(True)
+    t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(0, pts.data_ptr(), outb.data_ptr(), m, k), ctx.sync()), 3)
+    kms, kk = ctx.profile_read(lib.PROF_BATCH_MUL)
+    out["g1_batch_exp_2^%d" % (m.bit_length() - 1)] = {"ms": round(t, 3), "Mmul_per_s": round(m / t / 1e3, 2),
+                                                      "k_batch_mul_ms": round(kms / max(1, kk), 3),
+                                                      "hbm_GBps_algorithmic": round(128.0 * m / (t * 1e-3) / 1e9, 2)}
+    ctx.profile(False)
+    m2 = 1 << 20
+    p2 = make_points(torch, np, ctx, 1, m2, 1, device)
+    o2 = torch.empty(m2 * 128, dtype=torch.uint8, device=device)
+    t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), m2, k), ctx.sync()), 2)
+    out["g2_batch_exp_2^20"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2)}
+    # -- config 5 ingredient: G2 MSM at 2^20
+    t, _ = timed(torch, stream, lambda: ctx.msm_dev(1, p2.data_ptr(), sc.data_ptr(), m2), 3)
+    out["g2_msm_2^20"] = {"ms": round(t, 3), "Mscalar_mul_per_s": round(m2 / t / 1e3, 2)}
+    del p2, o2
+    # -- config 3: phase-2 contribute on a synthetic 2^20-constraint MPCParameters (h = 2^20 - 1, l = 2^20 points), host in / host out
+    nh, nl = (1 << 20) - 1, 1 << 20
+    if pts.numel() >= (nh + nl) * 64:
+        hl = pts[: (nh + nl) * 64].cpu().numpy().tobytes()
+        g1 = lambda i: hl[64 * i: 64 * i + 64]
+        g2 = G2_GEN
+        import hashlib
+        import struct
+        params = bytearray()
+        params += g1(0) + g1(1) + g2 + g2 + G1_GEN + g2                      # alpha_g1 beta_g1 beta_g2 gamma_g2 delta_g1 delta_g2
+        params += struct.pack(">I", 2) + g1(2) + g1(3)                        # ic
+        params += struct.pack(">I", nh) + hl[: nh * 64]                       # h
+        params += struct.pack(">I", nl) + hl[nh * 64: (nh + nl) * 64]         # l
+        params += struct.pack(">I", 16) + hl[: 16 * 64]                       # a
+        params += struct.pack(">I", 16) + hl[: 16 * 64]                       # b_g1
+        params += struct.pack(">I", 16) + g2 * 16                             # b_g2
+        params += hashlib.blake2b(b"bench").digest() + struct.pack(">I", 0)
+        pin = torch.empty(len(params), dtype=torch.uint8, pin_memory=True)
+        pin.copy_(torch.frombuffer(params, dtype=torch.uint8))
+        pout = torch.empty(len(params) + 384, dtype=torch.uint8, pin_memory=True)
+        times = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, h = ctx.phase2_contribute(pin.numpy(), k, np.frombuffer(g1(5), dtype=np.uint8), np.frombuffer(g2, dtype=np.uint8),
+                                         out=pout.numpy())
+            times.append(time.perf_counter() - t0)
+        out["phase2_contribute_2^20"] = {"wall_s": round(min(times), 4), "points": nh + nl, "params_bytes": len(params),
+                                         "contribution_hash": h.hex()[:32]}
+    # -- config 4: Fr FFT / iFFT at 2^24, round trip bit-exact
+    lf = 24
+    x = make_scalars(torch, 1 << lf, 0x3237db17, device)
+    y = x.clone()
+    ctx.fr_fft_dev(y.data_ptr(), lf, False, False); ctx.sync()
+    ctx.profile(True)
+    tf, _ = timed(torch, stream, lambda: (ctx.fr_fft_dev(y.data_ptr(), lf, True, False), ctx.fr_fft_dev(y.data_ptr(), lf, False, False)), 2)
+    pms, pk = ctx.profile_read(lib.PROF_FFT_PASS)
+    ctx.profile(False)
+    ctx.fr_fft_dev(y.data_ptr(), lf, True, False); ctx.sync()
+    ok = bool(torch.equal(x, y))
+    out["fr_fft_2^24"] = {"ms_per_transform": round(tf / 2, 3), "Melem_per_s": round((1 << lf) / (tf / 2) / 1e3, 1),
+                          "hbm_GBps_algorithmic": round(64.0 * (1 << lf) / (tf / 2 * 1e-3) / 1e9, 1),
+                          "pass_ms": round(pms / max(1, pk), 3), "round_trip_bit_exact": ok}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=26, help="log2 of the MSM terms per GPU")
+    ap.add_argument("--ref-log-n", type=int, default=20, help="log2 of the bounded CPU sample")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        run_reference(args, rank)
+        return
+    if world != args.gpus and rank == 0:
+        print("note: --gpus %d but WORLD_SIZE=%d; running %d rank(s)" % (args.gpus, world, world), file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,20 @@ void *p2b_stream(p2b_ctx *ctx);
 /* number of kernels this ctx has launched so far */
 uint64_t p2b_launch_count(p2b_ctx *ctx);
 const char *p2b_version(void);
+/* Profiling: when enabled, the ctx brackets its dominant kernels with CUDA events on p2b_stream(ctx) (the stream they
+ * are launched on).  p2b_profile_read waits for the stream and returns the summed device time and the number of kernel
+ * launches recorded in `slot` since p2b_profile_enable(ctx, 1) was last called (which also resets the counters). */
+enum {
+    P2B_PROF_BATCH_MUL = 0,      /* k_batch_mul: decode + scalar + [k]P */
+    P2B_PROF_NORMALIZE = 1,      /* k_normalize: batched inversion + encode */
+    P2B_PROF_MSM_SORT = 2,       /* prepare + histogram + scan + scatter */
+    P2B_PROF_MSM_ACCUMULATE = 3, /* bucket accumulation */
+    P2B_PROF_MSM_REDUCE = 4,     /* bucket / window reduction + final */
+    P2B_PROF_FFT_PASS = 5,       /* radix-256 FFT passes */
+    P2B_PROF_SLOTS = 6
+};
+int p2b_profile_enable(p2b_ctx *ctx, int on);
+int p2b_profile_read(p2b_ctx *ctx, int slot, double *total_ms, uint64_t *kernels);
 
 /* ---- level 1: batch_exp ---- */
 /* out[i] = [s_i] in[i];  n_scalars == n (one per point) or 1 (broadcast, phase-2 shape). */

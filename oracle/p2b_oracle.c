@@ -421,11 +421,19 @@ int orc_pot_transform(const uint8_t *challenge, uint64_t challenge_len, uint8_t 
 typedef struct {
     int g2; const uint8_t *points; int enc; const uint64_t (*ks)[4]; size_t n; unsigned c; unsigned nwin;
     void *accs; const void *affs;
+    size_t nchunks, next_task; pthread_mutex_t mu;
 } msm_ctx;
-static void msm_window(void *vp, size_t lo, size_t hi, int tid) {
-    (void)tid;
+/* Tasks are (window, point-chunk) pairs handed out dynamically, as bellman's CpuPool does for its per-window
+ * futures (multiexp.rs:75-145); with more workers than windows the points are also split into chunks whose
+ * per-window partial sums are merged under a mutex, as dense_multiexp_inner does (multiexp.rs:393-446). */
+static void msm_window(void *vp, size_t lo_unused, size_t hi_unused, int tid) {
+    (void)tid; (void)lo_unused; (void)hi_unused;
     msm_ctx *m = (msm_ctx *)vp;
-    for (size_t w = lo; w < hi; w++) {
+    for (;;) {
+        size_t task = __atomic_fetch_add(&m->next_task, 1, __ATOMIC_RELAXED);
+        if (task >= (size_t)m->nwin * m->nchunks) break;
+        size_t w = task / m->nchunks, ch = task % m->nchunks;
+        size_t per = (m->n + m->nchunks - 1) / m->nchunks, p_lo = ch * per, p_hi = p_lo + per < m->n ? p_lo + per : m->n;
         unsigned skip = (unsigned)w * m->c;
         size_t nb = ((size_t)1 << m->c) - 1;
         static const uint64_t one[4] = {1, 0, 0, 0};
@@ -434,7 +442,7 @@ static void msm_window(void *vp, size_t lo, size_t hi, int tid) {
             g1_jac acc = g1_jac_zero();
             g1_jac *b = (g1_jac *)malloc(nb * sizeof(g1_jac));
             for (size_t i = 0; i < nb; i++) b[i] = g1_jac_zero();
-            for (size_t i = 0; i < m->n; i++) {
+            for (size_t i = p_lo; i < p_hi; i++) {
                 if (r_is_zero(m->ks[i])) continue;
                 if (r_cmp(m->ks[i], one) == 0) { if (w == 0) g1_madd(&acc, &aff[i]); continue; }
                 uint64_t e[4] = {m->ks[i][0], m->ks[i][1], m->ks[i][2], m->ks[i][3]};
@@ -444,14 +452,16 @@ static void msm_window(void *vp, size_t lo, size_t hi, int tid) {
             }
             g1_jac run = g1_jac_zero();
             for (size_t i = nb; i-- > 0;) { g1_add(&run, &b[i]); g1_add(&acc, &run); }
-            ((g1_jac *)m->accs)[w] = acc;
+            pthread_mutex_lock(&m->mu);
+            g1_add(&((g1_jac *)m->accs)[w], &acc);
+            pthread_mutex_unlock(&m->mu);
             free(b);
         } else {
             const g2_aff *aff = (const g2_aff *)m->affs;
             g2_jac acc = g2_jac_zero();
             g2_jac *b = (g2_jac *)malloc(nb * sizeof(g2_jac));
             for (size_t i = 0; i < nb; i++) b[i] = g2_jac_zero();
-            for (size_t i = 0; i < m->n; i++) {
+            for (size_t i = p_lo; i < p_hi; i++) {
                 if (r_is_zero(m->ks[i])) continue;
                 if (r_cmp(m->ks[i], one) == 0) { if (w == 0) g2_madd(&acc, &aff[i]); continue; }
                 uint64_t e[4] = {m->ks[i][0], m->ks[i][1], m->ks[i][2], m->ks[i][3]};
@@ -461,7 +471,9 @@ static void msm_window(void *vp, size_t lo, size_t hi, int tid) {
             }
             g2_jac run = g2_jac_zero();
             for (size_t i = nb; i-- > 0;) { g2_add(&run, &b[i]); g2_add(&acc, &run); }
-            ((g2_jac *)m->accs)[w] = acc;
+            pthread_mutex_lock(&m->mu);
+            g2_add(&((g2_jac *)m->accs)[w], &acc);
+            pthread_mutex_unlock(&m->mu);
             free(b);
         }
     }
@@ -490,9 +502,13 @@ int orc_msm(int g2, const uint8_t *points, const uint8_t *scalars_be, size_t n, 
     parallel_ranges(n, threads, dec_range, &dc);
     if (dc.bad) { free(ks); free(affs); return ORC_EDECODE; }
     void *accs = malloc(nwin * (g2 ? sizeof(g2_jac) : sizeof(g1_jac)));
-    msm_ctx m = {g2, points, 0, (const uint64_t(*)[4])ks, n, c, nwin, accs, affs};
-    /* one task per window on up to `threads` workers */
-    parallel_ranges(nwin, threads > (int)nwin ? (int)nwin : threads, msm_window, &m);
+    for (unsigned w = 0; w < nwin; w++) {
+        if (g2) ((g2_jac *)accs)[w] = g2_jac_zero(); else ((g1_jac *)accs)[w] = g1_jac_zero();
+    }
+    if (threads < 1) threads = 1;
+    size_t nchunks = threads > (int)nwin && n >= 4096 ? ((size_t)threads + nwin - 1) / nwin : 1;
+    msm_ctx m = {g2, points, 0, (const uint64_t(*)[4])ks, n, c, nwin, accs, affs, nchunks, 0, PTHREAD_MUTEX_INITIALIZER};
+    parallel_ranges((size_t)threads, threads, msm_window, &m);     /* `threads` workers pulling tasks */
     if (!g2) {
         g1_jac *a = (g1_jac *)accs;
         g1_jac hi = a[nwin - 1];

@@ -36,6 +36,24 @@ int dev_reserve(Ctx *c, DevBuf &b, size_t bytes) {
     b.cap = cap;
     return P2B_OK;
 }
+void prof_begin(Ctx *c, int slot) {
+    if (!c->prof) return;
+    Ctx::ProfSlot &s = c->prof_slot[slot];
+    if (s.used == s.ev.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        s.ev.emplace_back(a, b);
+    }
+    cudaEventRecord(s.ev[s.used].first, c->stream);
+}
+void prof_end(Ctx *c, int slot, int kernels) {
+    if (!c->prof) return;
+    Ctx::ProfSlot &s = c->prof_slot[slot];
+    if (s.used >= s.ev.size()) return;
+    cudaEventRecord(s.ev[s.used].second, c->stream);
+    s.used++;
+    s.kernels += (uint64_t)kernels;
+}
 static int err_reset(Ctx *c) {
     P2B_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream));
     return P2B_OK;
@@ -438,6 +456,8 @@ void p2b_destroy(p2b_ctx *h) {
     DevBuf *bufs[] = {&c->jac, &c->prefix, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1], &c->scal,
                       &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->fft_tw};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (auto &sl : c->prof_slot)
+        for (auto &e : sl.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -455,6 +475,29 @@ void p2b_error_detail(p2b_ctx *h, uint64_t *index, int *sub) {
 }
 void *p2b_stream(p2b_ctx *h) { return h ? (void *)h->c.stream : nullptr; }
 uint64_t p2b_launch_count(p2b_ctx *h) { return h ? h->c.launches : 0; }
+
+int p2b_profile_enable(p2b_ctx *h, int on) {
+    if (!h) return P2B_EARG;
+    h->c.prof = on != 0;
+    for (auto &sl : h->c.prof_slot) { sl.used = 0; sl.kernels = 0; }
+    return P2B_OK;
+}
+int p2b_profile_read(p2b_ctx *h, int slot, double *total_ms, uint64_t *kernels) {
+    if (!h || slot < 0 || slot >= P2B_PROF_SLOTS) return P2B_EARG;
+    Ctx *c = &h->c;
+    P2B_CUDA(c, cudaSetDevice(c->device));
+    P2B_CUDA(c, cudaStreamSynchronize(c->stream));
+    double t = 0;
+    Ctx::ProfSlot &s = c->prof_slot[slot];
+    for (size_t i = 0; i < s.used; i++) {
+        float ms = 0;
+        P2B_CUDA(c, cudaEventElapsedTime(&ms, s.ev[i].first, s.ev[i].second));
+        t += ms;
+    }
+    if (total_ms) *total_ms = t;
+    if (kernels) *kernels = s.kernels;
+    return P2B_OK;
+}
 
 int p2b_g1_batch_mul(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) {
     return h ? host_batch(&h->c, 0, in, out, n, s, ns, ie, oe, fl) : P2B_EARG;

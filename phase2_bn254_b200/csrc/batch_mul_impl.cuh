@@ -276,14 +276,18 @@ template <class F, int BLOCK> int launch_typed(Ctx *c, const void *d_in, void *d
     size_t ntiles = (n + BLOCK - 1) / BLOCK;
     int grid = (int)(ntiles < (size_t)c->sm_count ? ntiles : (size_t)c->sm_count);
     if (grid > 0) {
+        prof_begin(c, P2B_PROF_BATCH_MUL);
         k_batch_mul<F, BLOCK><<<grid, BLOCK, smem, c->stream>>>(bp);
+        prof_end(c, P2B_PROF_BATCH_MUL, 1);
         c->launches++;
         // ~32 points per thread in the normalisation pass, at least one full wave of 128-thread blocks
         size_t threads = (n + 31) / 32;
         if (threads < (size_t)c->sm_count * 128) threads = n < (size_t)c->sm_count * 128 ? n : (size_t)c->sm_count * 128;
         int nblocks = (int)((threads + 127) / 128);
         NormalizeParams np{jx, jy, jz, (uint32_t *)c->prefix.p, (uint32_t *)d_out, n, out_enc, flags, c->d_err, err_base};
+        prof_begin(c, P2B_PROF_NORMALIZE);
         k_normalize<F><<<nblocks, 128, 0, c->stream>>>(np);
+        prof_end(c, P2B_PROF_NORMALIZE, 1);
         c->launches++;
     }
     P2B_CUDA(c, cudaGetLastError());

@@ -217,7 +217,9 @@ template <bool FIRST, bool LAST> static int fft_launch_pass(Ctx *c, const FftPas
         P2B_CUDA(c, cudaFuncSetAttribute(k_fft_pass<FIRST, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr = true;
     }
+    prof_begin(c, P2B_PROF_FFT_PASS);
     k_fft_pass<FIRST, LAST><<<blocks, FFT_BLOCK, smem, c->stream>>>(p);
+    prof_end(c, P2B_PROF_FFT_PASS, 1);
     c->launches++;
     return P2B_OK;
 }

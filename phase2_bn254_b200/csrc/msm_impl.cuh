@@ -368,15 +368,21 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     int grid = (int)((n + 255) / 256);
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
     if (grid < 1) grid = 1;
+    prof_begin(c, P2B_PROF_MSM_SORT);
     k_msm_prepare<F><<<grid, 256, 0, c->stream>>>((const uint32_t *)d_points, aff, n, c->d_err);
     k_msm_hist<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err);
     k_msm_scan<<<1, 1024, 0, c->stream>>>(hist, offsets, cursor, (uint32_t)nslots);
     k_msm_scatter<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, cursor, sorted);
+    prof_end(c, P2B_PROF_MSM_SORT, 4);
     int agrid = (int)((nslots + 127) / 128);
+    prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
     k_msm_accumulate<F><<<agrid, 128, 0, c->stream>>>(aff, offsets, sorted, g, buckets);
+    prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
+    prof_begin(c, P2B_PROF_MSM_REDUCE);
     k_msm_reduce1<F><<<(int)((nred + 127) / 128), 128, 0, c->stream>>>(buckets, g, s1, s2);
     k_msm_reduce2<F><<<g.nwin, 256, 0, c->stream>>>(s1, s2, g, wsum);
     k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
+    prof_end(c, P2B_PROF_MSM_REDUCE, 3);
     c->launches += 8;
     P2B_CUDA(c, cudaGetLastError());
     return P2B_OK;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
+#include <vector>
 #include "../../include/p2b.h"
 
 namespace p2b {
@@ -33,6 +35,13 @@ struct Ctx {
     void *h_pin[2] = {nullptr, nullptr};
     size_t h_pin_cap[2] = {0, 0};
     cudaEvent_t ev[8] = {};
+    // profiling (p2b_profile_enable): CUDA-event brackets around the dominant kernels, on `stream`
+    bool prof = false;
+    struct ProfSlot {
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+        size_t used = 0;
+        uint64_t kernels = 0;
+    } prof_slot[P2B_PROF_SLOTS];
     // cached FFT twiddle state
     uint32_t fft_tw_log_n = 0;
     int fft_tw_inverse = -1;
@@ -43,6 +52,10 @@ int ctx_cuda(Ctx *c, cudaError_t e, const char *what);
 int dev_reserve(Ctx *c, DevBuf &b, size_t bytes);
 // reads the device error word back (after the stream has drained) and converts it to a P2B_* code
 int ctx_collect_error(Ctx *c);
+
+// brackets `kernels` launches queued between prof_begin / prof_end with timing events (no-ops unless profiling)
+void prof_begin(Ctx *c, int slot);
+void prof_end(Ctx *c, int slot, int kernels);
 
 #define P2B_CUDA(c, call)                                     \
     do {                                                      \

@@ -1,0 +1,61 @@
+"""One-process-per-GPU plumbing for the parts of the hot path that shard.
+
+  batch_exp (transform / contribute)  contiguous index ranges per rank, disjoint output bytes, NO collective
+  Pippenger MSM                       shard by point range; every rank reduces its shard to ONE affine point on its
+                                      GPU, the ranks all-gather those 64 / 128-byte results (NCCL has no reduce op
+                                      for elliptic-curve addition) and each adds the `world` points locally
+  Fr FFT                              does not shard at ceremony sizes: replicas only
+
+The reference has no distributed layer (single process, crossbeam threads over `len / num_cpus` chunks,
+powersoftau/src/batched_accumulator.rs:1137-1162, bellman/src/multicore.rs:55-71); `shard_range` is the same static
+range split applied to ranks instead of threads.
+"""
+import numpy as np
+
+from . import lib as _lib
+
+
+def shard_range(count, index, shards):
+    """[lo, hi) of shard `index`: contiguous, sizes differ by at most one, identical to the C ABI's split
+    (csrc/api.cu shard_range) used by p2b_pot_transform."""
+    per, rem = divmod(count, shards)
+    lo = per * index + min(index, rem)
+    return lo, lo + per + (1 if index < rem else 0)
+
+
+def all_gather_bytes(payload, group=None, device=None):
+    """All-gather of one fixed-size byte string per rank over torch.distributed (NCCL on GPUs, gloo on CPU).
+    Returns the concatenation in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * t.numel(), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().tobytes()
+
+
+def sharded_msm(ctx, group_id, local_points, local_scalars, n_local, group=None, device=None, on_device=False):
+    """sum over ALL ranks' terms of scalar * point.  Each rank passes only its own shard (host buffers, or device
+    pointers with on_device=True); every rank returns the same uncompressed wire point."""
+    if on_device:
+        part = ctx.msm_dev(group_id, local_points, local_scalars, n_local)
+    else:
+        part = ctx.msm(group_id, local_points, local_scalars)
+    parts = all_gather_bytes(part, group=group, device=device)
+    return ctx.sum_points(group_id, np.frombuffer(parts, dtype=np.uint8))
+
+
+def sharded_transform(ctx, input_map, output_map, parameters, key, rank, world, input_is_compressed=False,
+                      compress_the_output=True, check_input_for_correctness=False):
+    """BatchedAccumulator::transform with every section split across `world` ranks (no collective: rank r writes
+    only its own byte ranges of output_map, which must be shared storage such as the response mmap)."""
+    from .powersoftau import BatchedAccumulator
+    BatchedAccumulator.transform(input_map, output_map, input_is_compressed, compress_the_output,
+                                 check_input_for_correctness, key, parameters, ctx=ctx, shard_index=rank,
+                                 shard_count=world)
+
+
+__all__ = ["shard_range", "all_gather_bytes", "sharded_msm", "sharded_transform", "_lib"]

@@ -25,8 +25,9 @@ SYMBOLS = [
     "p2b_g1_batch_mul_powers_dev", "p2b_g2_batch_mul_powers_dev", "p2b_sync",
     "p2b_pot_accumulator_size", "p2b_pot_transform", "p2b_phase2_transcript", "p2b_phase2_contribute",
     "p2b_g1_msm", "p2b_g2_msm", "p2b_g1_msm_dev", "p2b_g2_msm_dev", "p2b_g1_sum_points", "p2b_g2_sum_points",
-    "p2b_fr_fft", "p2b_fr_fft_dev",
+    "p2b_fr_fft", "p2b_fr_fft_dev", "p2b_profile_enable", "p2b_profile_read",
 ]
+PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
 
 class P2BError(RuntimeError):
@@ -81,6 +82,8 @@ def load():
     if hasattr(lib, "p2b_fr_fft"):
         lib.p2b_fr_fft.argtypes = [vp, u8p, u32, i32, i32]
         lib.p2b_fr_fft_dev.argtypes = [vp, vp, u32, i32, i32]
+    lib.p2b_profile_enable.argtypes = [vp, i32]
+    lib.p2b_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     _lib = lib
     return lib
 
@@ -142,6 +145,16 @@ class Context:
 
     def sync(self):
         self._check(self.lib.p2b_sync(self.h))
+
+    def profile(self, on=True):
+        """Bracket the dominant kernels with CUDA events on the ctx stream (and reset the counters)."""
+        self._check(self.lib.p2b_profile_enable(self.h, int(on)))
+
+    def profile_read(self, slot):
+        """(total device ms, kernel launches) recorded in `slot` since profile(True)."""
+        ms, k = ctypes.c_double(0), ctypes.c_uint64(0)
+        self._check(self.lib.p2b_profile_read(self.h, slot, ctypes.byref(ms), ctypes.byref(k)))
+        return ms.value, k.value
 
     # -- level 1 (host buffers)
     def batch_mul(self, group, points, scalars, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0, out=None):

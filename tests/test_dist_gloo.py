@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the N > 1 host logic -- range sharding, the all-gather of per-rank MSM results and
+their combination -- with the oracle standing in for the per-rank GPU compute (checker-only use)."""
+import os
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleCtx:
+    """Duck-typed stand-in for lib.Context in a GPU-less test: same msm / sum_points contract, CPU oracle inside."""
+
+    def __init__(self, oc):
+        self.oc = oc
+
+    def msm(self, group, points, scalars):
+        return self.oc.msm(group, bytes(points), bytes(scalars), threads=2)
+
+    def sum_points(self, group, points):
+        return self.oc.sum_points(group, bytes(points))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import oracle as oc
+    from phase2_bn254_b200 import dist as pdist
+    from util import random_points, random_scalars
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        res = {}
+        for group, n in ((0, 301), (1, 77)):
+            size = 128 if group else 64
+            pts, sc = random_points(oc, group, n, seed=5, threads=2), random_scalars(n, seed=6)   # same on all ranks
+            lo, hi = pdist.shard_range(n, rank, world)
+            got = pdist.sharded_msm(OracleCtx(oc), group, pts[lo * size:hi * size], sc[lo * 32:hi * 32], hi - lo)
+            res[group] = (got, oc.msm(group, pts, sc, threads=2))
+        gathered = pdist.all_gather_bytes(bytes([rank]) * 64)
+        q.put((rank, res, gathered))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_msm_world2():
+    world, port = 2, 29500 + os.getpid() % 500
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res, gathered in out:
+        for group in (0, 1):
+            got, exp = res[group]
+            assert got == exp, "rank %d group %d" % (rank, group)
+        assert gathered == bytes([0]) * 64 + bytes([1]) * 64
+
+
+def test_shard_range_partition():
+    sys.path.insert(0, ROOT)
+    from phase2_bn254_b200.dist import shard_range
+    for count in (0, 1, 7, 8, 2047, 1 << 20):
+        for shards in (1, 2, 3, 8):
+            edges = [shard_range(count, i, shards) for i in range(shards)]
+            assert edges[0][0] == 0 and edges[-1][1] == count
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
