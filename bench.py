@@ -314,8 +314,16 @@ def run_ours(args, rank, world, local_rank):
             line["extras"] = extras(args, torch, np, ctx, stream, device, lib, pts, sc)
         del pts, sc
         torch.cuda.empty_cache()
+        pot10 = line.get("extras", {}).pop("_pot10", None)
         if not args.no_cpu:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            if pot10:   # config 1: 2^10 challenge on ONE CPU thread (the reference's own runnable case) vs the GPU response
+                import oracle as oc
+                chb, key, body = pot10
+                t0 = time.perf_counter()
+                exp = oc.pot_transform(chb, 10, 256, be(key.tau), be(key.alpha), be(key.beta), threads=1)
+                line["extras"]["pot_transform_2^10"].update({"cpu_1thread_s": round(time.perf_counter() - t0, 3),
+                                                             "response_matches_oracle": exp[64:] == body})
             rate, dt, cores = cpu_msm_rate(args.ref_log_n)
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "one Pippenger MSM over 2^%d of the workload's terms (%.1f s), oracle/p2b_oracle.c "
@@ -338,6 +346,7 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
     # -- batch_exp (the transform / contribute hot loop), device resident, 2^22 G1 and 2^20 G2
     m = min(1 << 22, pts.numel() // 64)
     outb = torch.empty(m * 64, dtype=torch.uint8, device=device)
+    ctx.batch_mul_dev(0, pts.data_ptr(), outb.data_ptr(), m, k); ctx.sync()
     ctx.profile(True)
     t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(0, pts.data_ptr(), outb.data_ptr(), m, k), ctx.sync()), 3)
     kms, kk = ctx.profile_read(lib.PROF_BATCH_MUL)
@@ -348,9 +357,15 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
     m2 = 1 << 20
     p2 = make_points(torch, np, ctx, 1, m2, 1, device)
     o2 = torch.empty(m2 * 128, dtype=torch.uint8, device=device)
+    ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), 1024, k); ctx.sync()
     t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), m2, k), ctx.sync()), 2)
     out["g2_batch_exp_2^20"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2)}
+    ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), 1024, k, flags=lib.G2_SUBGROUP); ctx.sync()
+    t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), m2, k, flags=lib.G2_SUBGROUP), ctx.sync()), 2)
+    out["g2_batch_exp_2^20_subgroup_flag"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2),
+                                              "note": "opt-in endomorphism split (P2B_G2_SUBGROUP)"}
     # -- config 5 ingredient: G2 MSM at 2^20
+    ctx.msm_dev(1, p2.data_ptr(), sc.data_ptr(), m2)
     t, _ = timed(torch, stream, lambda: ctx.msm_dev(1, p2.data_ptr(), sc.data_ptr(), m2), 3)
     out["g2_msm_2^20"] = {"ms": round(t, 3), "Mscalar_mul_per_s": round(m2 / t / 1e3, 2)}
     del p2, o2
@@ -383,6 +398,37 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
             times.append(time.perf_counter() - t0)
         out["phase2_contribute_2^20"] = {"wall_s": round(min(times), 4), "points": nh + nl, "params_bytes": len(params),
                                          "contribution_hash": h.hex()[:32]}
+    # -- configs 1 / phase-1 hot path: BatchedAccumulator::transform on the deterministic initial challenge (all generators,
+    #    new_constrained), host maps in / out, compressed response; Blake2b-512 of the response body = "response hash"
+    import hashlib
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    key = PrivateKey(TAU, 0x2222 * 2**190 % R_MOD, 0x3333 * 2**180 % R_MOD)
+    for size in (10, 20):
+        prm = CeremonyParams(size, 256)
+        pl, pg1 = prm.powers_length, prm.powers_g1_length
+        ch = torch.empty(prm.accumulator_size, dtype=torch.uint8, pin_memory=True)
+        chn = ch.numpy()
+        chn[:64] = np.frombuffer(hashlib.blake2b(b"").digest(), dtype=np.uint8)
+        g1a, g2a = np.frombuffer(G1_GEN, dtype=np.uint8), np.frombuffer(G2_GEN, dtype=np.uint8)
+        o = 64
+        for cnt, g in ((pg1, g1a), (pl, g2a), (pl, g1a), (pl, g1a), (1, g2a)):
+            chn[o:o + cnt * g.size].reshape(cnt, g.size)[:] = g
+            o += cnt * g.size
+        rs = torch.zeros(prm.contribution_size, dtype=torch.uint8, pin_memory=True)
+        rsn = rs.numpy()
+        times = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            BatchedAccumulator.transform(chn, rsn, False, True, False, key, prm, ctx=ctx)
+            times.append(time.perf_counter() - t0)
+        end = prm.contribution_size - prm.public_key_size
+        out["pot_transform_2^%d" % size] = {"wall_s": round(min(times), 4), "g1_points": pg1 + 2 * pl, "g2_points": pl + 1,
+                                            "challenge_bytes": prm.accumulator_size,
+                                            "response_body_blake2b": hashlib.blake2b(rsn[64:end].tobytes()).hexdigest()[:32]}
+        if size == 10:
+            out["_pot10"] = (chn.tobytes(), key, rsn[64:end].tobytes())
+        del ch, rs
     # -- config 4: Fr FFT / iFFT at 2^24, round trip bit-exact
     lf = 24
     x = make_scalars(torch, 1 << lf, 0x3237db17, device)

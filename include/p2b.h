@@ -59,7 +59,11 @@ enum { /* decode sub-codes */
 enum { P2B_ENC_UNCOMPRESSED = 0, P2B_ENC_COMPRESSED = 1, P2B_ENC_RAW_MONT_LE = 2 };
 enum { /* flags */
     P2B_CHECK_INPUT = 1,     /* CheckForCorrectness::Yes: is_on_curve on every decoded point */
-    P2B_REJECT_INFINITY = 2  /* infinity in the input or the output is an error (phase-1 semantics) */
+    P2B_REJECT_INFINITY = 2, /* infinity in the input or the output is an error (phase-1 semantics) */
+    P2B_G2_SUBGROUP = 4      /* the caller vouches that every G2 input lies in the order-r subgroup (true for any point
+                                produced by scalar multiplication of the generator): enables the endomorphism-split G2
+                                path (~1.4x faster).  Without it G2 results are exact for EVERY on-curve point, like the
+                                reference, which decodes G2 without a subgroup check (pairing/src/bn256/ec.rs:1145-1213). */
 };
 
 /* ---- context ---- */
@@ -120,7 +124,8 @@ uint64_t p2b_pot_accumulator_size(uint32_t size_log2, int compressed);
 /* Writes the accumulator region [64, accumulator_size(out)) of `response` exactly as write_chunk would.  Bytes [0,64)
  * (hash of the challenge) and the trailing public key stay with the caller (compute_constrained.rs:155-161,207-209).
  * [shard_index, shard_count): this process transforms only its contiguous share of every section (one process per
- * GPU; shards write disjoint byte ranges of `response`); pass 0, 1 for the whole file. */
+ * GPU; shards write disjoint byte ranges of `response`); pass 0, 1 for the whole file.
+ * check_input: 0 / 1 = CheckForCorrectness::{No, Yes}; may be OR-ed with P2B_G2_SUBGROUP (see the flag). */
 int p2b_pot_transform(p2b_ctx *ctx, const uint8_t *challenge, uint64_t challenge_len, uint8_t *response,
                       uint64_t response_len, uint32_t size_log2, uint32_t batch_size, int in_compressed,
                       int out_compressed, int check_input, const uint8_t tau_be[32], const uint8_t alpha_be[32],

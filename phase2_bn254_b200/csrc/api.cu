@@ -7,6 +7,7 @@
 // 3-stream pipeline (H2D | compute | D2H, double buffered) -- the GPU analogue of the reference's out-of-core
 // chunk loop over two mmaps (batched_accumulator.rs:1187,1242).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "blake2b.h"
@@ -256,7 +257,7 @@ static int pot_transform(Ctx *c, const uint8_t *challenge, uint64_t challenge_le
     const uint64_t g1i = in_c ? 32 : 64, g2i = in_c ? 64 : 128, g1o = out_c ? 32 : 64, g2o = out_c ? 64 : 128;
     // section order in both files: TauG1, TauG2, AlphaG1, BetaG1, BetaG2 (batched_accumulator.rs:87-94,96-178)
     const Section sections[4] = {{0, powers_g1, 0}, {1, powers, 0}, {0, powers, 1}, {0, powers, 2}};
-    const int flags = (check ? P2B_CHECK_INPUT : 0) | P2B_REJECT_INFINITY;
+    const int flags = ((check & 1) ? P2B_CHECK_INPUT : 0) | P2B_REJECT_INFINITY | (check & P2B_G2_SUBGROUP);
     int rc = begin_call(c);
     if (rc) return rc;
     uint64_t ioff = 64, ooff = 64;
@@ -431,6 +432,7 @@ int p2b_init(int device, p2b_ctx **out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return P2B_ECUDA;
     if (cudaSetDevice(device) != cudaSuccess) return P2B_ECUDA;
+    if (const char *e = getenv("P2B_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // tuning hook
     p2b_ctx *h = new p2b_ctx();
     Ctx *c = &h->c;
     c->device = device;
@@ -454,7 +456,7 @@ void p2b_destroy(p2b_ctx *h) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->jac, &c->prefix, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1], &c->scal,
-                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->fft_tw};
+                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->fft_tw, &c->gtable};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &sl : c->prof_slot)
         for (auto &e : sl.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }

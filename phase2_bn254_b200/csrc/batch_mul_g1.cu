@@ -26,12 +26,16 @@ int read_scalar_be(const uint8_t *be, uint32_t k[8]) {
 int launch_batch_mul_g2(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc, int out_enc,
                         int flags, uint64_t err_index_base);
 
+int launch_batch_mul_g2_glv(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc, int out_enc,
+                            int flags, uint64_t err_index_base);
+
 int launch_batch_mul(Ctx *c, int g2, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc,
                      int out_enc, int flags, uint64_t err_index_base) {
     if (n == 0) return P2B_OK;
     if (in_enc < 0 || in_enc > 2 || out_enc < 0 || out_enc > 2) return ctx_fail(c, P2B_EARG, "bad encoding");
+    if (g2 && (flags & P2B_G2_SUBGROUP)) return launch_batch_mul_g2_glv(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
     if (g2) return launch_batch_mul_g2(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
-    return launch_typed<Fq, G1_BLOCK>(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
+    return launch_typed<Fq, G1_BLOCK, true>(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
 }
 
 }  // namespace p2b

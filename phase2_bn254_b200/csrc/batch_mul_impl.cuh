@@ -118,14 +118,40 @@ struct BatchMulParams {
     uint64_t start;            // mode 2
     unsigned long long *err;
     uint64_t err_base;
+    uint4 *gtable;             // G2: per-thread odd-multiples tables in global memory (grid * block columns)
 };
 
-template <class F, int BLOCK> __global__ void __launch_bounds__(BLOCK, 1) k_batch_mul(BatchMulParams p) {
+// table policy: G1 keeps its 512 B / thread table in shared memory; G2 (1 KB / thread) keeps it in L2 so that two
+// 128-thread blocks fit on an SM
+template <class F, int BLOCK> struct TablePolicy;
+#ifndef P2B_G1_BLOCK
+#define P2B_G1_BLOCK 256
+#endif
+#ifndef P2B_G1_MIN_BLOCKS
+#define P2B_G1_MIN_BLOCKS 1
+#endif
+template <int BLOCK> struct TablePolicy<Fq, BLOCK> {
+    static constexpr int MIN_BLOCKS = P2B_G1_MIN_BLOCKS;
+    static constexpr size_t SMEM = (size_t)BLOCK * 8 * 2 * 8 * 4;
+    static __device__ __forceinline__ StridedTable<Fq> make(uint32_t *smem, const BatchMulParams &) {
+        return StridedTable<Fq>{smem + threadIdx.x, BLOCK};   // private column: no barriers needed anywhere in this kernel
+    }
+};
+template <int BLOCK> struct TablePolicy<Fq2, BLOCK> {
+    static constexpr int MIN_BLOCKS = 2;
+    static constexpr size_t SMEM = 0;
+    static __device__ __forceinline__ GlobalTable<Fq2> make(uint32_t *, const BatchMulParams &p) {
+        return GlobalTable<Fq2>{p.gtable + (size_t)blockIdx.x * BLOCK + threadIdx.x, (size_t)gridDim.x * BLOCK};
+    }
+};
+
+// GLV: use the endomorphism split (always for G1; for G2 only when the caller vouches for subgroup membership)
+template <class F, int BLOCK, bool GLV> __global__ void __launch_bounds__(BLOCK, TablePolicy<F, BLOCK>::MIN_BLOCKS) k_batch_mul(BatchMulParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     constexpr bool IS_G1 = FieldTraits<F>::WORDS == 8;
     const int tid = threadIdx.x;
-    StridedTable<F> tbl{smem + tid, BLOCK};     // private column: no barriers needed anywhere in this kernel
+    const auto tbl = TablePolicy<F, BLOCK>::make(smem, p);
     const size_t ntiles = (p.n + BLOCK - 1) / BLOCK;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t i = tile * BLOCK + tid;
@@ -137,7 +163,7 @@ template <class F, int BLOCK> __global__ void __launch_bounds__(BLOCK, 1) k_batc
         bool inf;
         int rc = point_decode<F>(a, inf, w, p.in_enc, false);
         bool oncurve = true;
-        if (!rc && !inf && (IS_G1 || (p.flags & P2B_CHECK_INPUT))) oncurve = on_curve(a);
+        if (!rc && !inf && (GLV || (p.flags & P2B_CHECK_INPUT))) oncurve = on_curve(a);
         if (!rc && !oncurve && (p.flags & P2B_CHECK_INPUT)) rc = DEC_NOT_ON_CURVE;
         if (rc) { report(p.err, p.err_base + i, P2B_EDECODE, rc); inf = true; }
         else if (inf && (p.flags & P2B_REJECT_INFINITY)) report(p.err, p.err_base + i, P2B_EINFINITY_IN, 0);
@@ -169,9 +195,9 @@ template <class F, int BLOCK> __global__ void __launch_bounds__(BLOCK, 1) k_batc
             r = jac_infinity<F>();
         } else {
             F zr[8];
-            bool bad = !oncurve;      // G1 off-curve garbage (unchecked mode): GLV does not apply
+            bool bad = !oncurve;      // off-curve garbage (unchecked mode): GLV does not apply
             if (!bad) {
-                if constexpr (IS_G1) r = g1_mul_glv(a, k, tbl, zr, bad);
+                if constexpr (GLV) r = mul_glv<F>(a, k, tbl, zr, bad);
                 else r = mul_window4<F>(a, k, tbl, zr, bad);
             }
             if (bad) mul_binary_slow<F>(&r, &a, k);
@@ -226,10 +252,10 @@ template <class F> __global__ void __launch_bounds__(128) k_normalize(NormalizeP
         if (i < T) break;
     }
 }
-static constexpr int G1_BLOCK = 256;
+static constexpr int G1_BLOCK = P2B_G1_BLOCK;
 static constexpr int G2_BLOCK = 128;
 
-template <class F, int BLOCK> int launch_typed(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc,
+template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc,
                                                        int in_enc, int out_enc, int flags, uint64_t err_base) {
     constexpr int W = FieldTraits<F>::WORDS;
     constexpr bool IS_G2 = W == 16;
@@ -267,17 +293,22 @@ template <class F, int BLOCK> int launch_typed(Ctx *c, const void *d_in, void *d
         bp.tables = (const Fr *)c->tables.p;
         bp.start = sc.start;
     }
-    const size_t smem = (size_t)BLOCK * 8 * 2 * W * 4;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[IS_G2]) {
-        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[IS_G2] = true;
+    const size_t smem = TablePolicy<F, BLOCK>::SMEM;
+    static bool attr_set = false;
+    if (!attr_set && smem) {
+        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
     }
     size_t ntiles = (n + BLOCK - 1) / BLOCK;
-    int grid = (int)(ntiles < (size_t)c->sm_count ? ntiles : (size_t)c->sm_count);
+    const size_t max_grid = (size_t)c->sm_count * TablePolicy<F, BLOCK>::MIN_BLOCKS;
+    int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
+    if (IS_G2) {
+        if ((rc = dev_reserve(c, c->gtable, max_grid * BLOCK * 8 * 2 * W * 4))) return rc;
+        bp.gtable = (uint4 *)c->gtable.p;
+    }
     if (grid > 0) {
         prof_begin(c, P2B_PROF_BATCH_MUL);
-        k_batch_mul<F, BLOCK><<<grid, BLOCK, smem, c->stream>>>(bp);
+        k_batch_mul<F, BLOCK, GLV><<<grid, BLOCK, smem, c->stream>>>(bp);
         prof_end(c, P2B_PROF_BATCH_MUL, 1);
         c->launches++;
         // ~32 points per thread in the normalisation pass, at least one full wave of 128-thread blocks

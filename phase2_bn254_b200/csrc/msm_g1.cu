@@ -2,7 +2,8 @@
 #include "msm_impl.cuh"
 
 namespace p2b {
-int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire);
+int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire, size_t geom_n,
+                 int phase, uint64_t err_base);
 void launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
 
 // result: uncompressed wire bytes in device memory c->misc (first 128 bytes)
@@ -10,7 +11,8 @@ static int msm_run(Ctx *c, int g2, const void *d_points, const void *d_scalars, 
     int rc;
     if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
     uint32_t *d_out = (uint32_t *)c->misc.p;
-    rc = g2 ? msm_typed_g2(c, d_points, d_scalars, n, d_out) : msm_typed<Fq>(c, d_points, d_scalars, n, d_out);
+    rc = g2 ? msm_typed_g2(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0)
+            : msm_typed<Fq>(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0);
     if (rc) return rc;
     P2B_CUDA(c, cudaMemcpyAsync(out_host, d_out, g2 ? 128 : 64, cudaMemcpyDeviceToHost, c->stream));
     return ctx_collect_error(c);
@@ -23,10 +25,48 @@ static int msm_begin(Ctx *c) {
     return P2B_OK;
 }
 
+// Host buffers larger than STREAM_MIN terms are streamed: chunks of STREAM_CHUNK terms are copied on the H2D stream into
+// a double-buffered staging area while the previous chunk is sorted and accumulated into the SAME buckets; the bucket
+// reduction runs once at the end.  The sum is unchanged (bucket contents are sums of the same terms).
+static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 24;
+static size_t msm_stream_chunk() {       // P2B_MSM_STREAM_CHUNK=<terms>: test hook to exercise the streamed path at small sizes
+    const char *e = getenv("P2B_MSM_STREAM_CHUNK");
+    long v = e ? atol(e) : 0;
+    return v > 0 ? (size_t)v : 0;
+}
+static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
+    const size_t ov = msm_stream_chunk();
+    const size_t psz = g2 ? 128 : 64, chunk = ov ? ov : MSM_STREAM_CHUNK, nchunks = (n + chunk - 1) / chunk;
+    int rc;
+    for (int b = 0; b < 2; b++)
+        if ((rc = dev_reserve(c, c->stage_in[b], chunk * (psz + 32)))) return rc;
+    if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
+    uint32_t *d_out = (uint32_t *)c->misc.p;
+    cudaEvent_t *ev_in = c->ev, *ev_done = c->ev + 2;
+    P2B_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        const int b = (int)(ci & 1);
+        const size_t off = ci * chunk, m = off + chunk <= n ? chunk : n - off;
+        P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, ci >= 2 ? ev_done[b] : c->ev[6], 0));
+        char *d_pts = (char *)c->stage_in[b].p, *d_sc = d_pts + chunk * psz;
+        P2B_CUDA(c, cudaMemcpyAsync(d_pts, points + off * psz, m * psz, cudaMemcpyHostToDevice, c->copy_in));
+        P2B_CUDA(c, cudaMemcpyAsync(d_sc, scalars + off * 32, m * 32, cudaMemcpyHostToDevice, c->copy_in));
+        P2B_CUDA(c, cudaEventRecord(ev_in[b], c->copy_in));
+        P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
+        const int phase = (ci == 0 ? MSM_FIRST : 0) | (ci + 1 == nchunks ? MSM_LAST : 0);
+        rc = g2 ? msm_typed_g2(c, d_pts, d_sc, m, d_out, chunk, phase, off) : msm_typed<Fq>(c, d_pts, d_sc, m, d_out, chunk, phase, off);
+        if (rc) return rc;
+        P2B_CUDA(c, cudaEventRecord(ev_done[b], c->stream));
+    }
+    P2B_CUDA(c, cudaMemcpyAsync(out, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
+    return ctx_collect_error(c);
+}
+
 static int msm_host(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
     if (!out || (n && (!points || !scalars))) return ctx_fail(c, P2B_EARG, "null buffer");
     int rc = msm_begin(c);
     if (rc) return rc;
+    if (n > (msm_stream_chunk() ? msm_stream_chunk() : MSM_STREAM_MIN)) return msm_host_streamed(c, g2, points, scalars, n, out);
     const size_t psz = g2 ? 128 : 64;
     if ((rc = dev_reserve(c, c->stage_in[0], (n ? n : 1) * psz))) return rc;
     if ((rc = dev_reserve(c, c->stage_in[1], (n ? n : 1) * 32))) return rc;

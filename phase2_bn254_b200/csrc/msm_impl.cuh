@@ -18,6 +18,8 @@
 // Signed digits halve the bucket count: digit d in (-2^(c-1), 2^(c-1)], bucket |d|, sign folded into the point's y.
 #pragma once
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "codec.cuh"
 #include "xyzz.cuh"
@@ -76,13 +78,18 @@ template <class F> __device__ __forceinline__ Xyzz<F> shfl_xyzz(const Xyzz<F> &p
 
 // ------------------------------------------------------------------------------------------------- parameters
 struct MsmGeom {
-    uint32_t c;        // window bits
+    uint32_t c;        // window bits of the wide windows; windows [0, nnarrow) are one bit narrower (balanced split of 255 bits)
+    uint32_t nnarrow;
     uint32_t nwin;     // number of windows
     uint32_t nb;       // buckets per window = 2^(c-1); bucket ids 1..nb (slot 0 unused)
     uint32_t nbk;      // nb + 1
     uint32_t strip;    // buckets per reduce1 thread
     uint32_t tpw;      // reduce threads per window = nb / strip (multiple of 32, <= 1024)
 };
+__host__ __device__ __forceinline__ uint32_t win_width(const MsmGeom &g, uint32_t w) { return w < g.nnarrow ? g.c - 1 : g.c; }
+__host__ __device__ __forceinline__ uint32_t win_off(const MsmGeom &g, uint32_t w) {
+    return w < g.nnarrow ? w * (g.c - 1) : g.nnarrow * (g.c - 1) + (w - g.nnarrow) * g.c;
+}
 __device__ __forceinline__ void scalar_words(uint32_t k[8], const uint32_t *scalars, size_t i) {
     uint32_t w[8];
     ldw<8>(w, scalars + i * 8);
@@ -102,7 +109,7 @@ static __device__ __forceinline__ void report_err(unsigned long long *err, uint6
 }
 
 // ------------------------------------------------------------------------------------------------- kernels
-template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const uint32_t *wire, uint32_t *aff, size_t n, unsigned long long *err) {
+template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const uint32_t *wire, uint32_t *aff, size_t n, unsigned long long *err, uint64_t err_base) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t w[WU];
@@ -110,26 +117,27 @@ template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const ui
         Aff<F> a;
         bool inf;
         int rc = point_decode<F>(a, inf, w, ENC_UNCOMPRESSED, false);
-        if (rc) { report_err(err, i, P2B_EDECODE, rc); inf = true; }
+        if (rc) { report_err(err, err_base + i, P2B_EDECODE, rc); inf = true; }
         uint32_t o[WU];
         point_encode<F>(o, a, inf, ENC_RAW_MONT_LE);   // infinity = all-zero: skipped by the accumulator
         stw<WU>(aff + i * WU, o);
     }
 }
 
-static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *hist, unsigned long long *err) {
+static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *hist, unsigned long long *err, uint64_t err_base) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t k[8];
         scalar_words(k, scalars, i);
         Fr kc;
 #pragma unroll
         for (int j = 0; j < 8; j++) kc.l[j] = k[j];
-        if (!is_canonical(kc)) report_err(err, i, P2B_EARG, 0);
+        if (!is_canonical(kc)) report_err(err, err_base + i, P2B_EARG, 0);
         uint32_t carry = 0;
         for (uint32_t w = 0; w < g.nwin; w++) {
-            uint32_t d = raw_window(k, w * g.c, g.c) + carry;
-            carry = d > g.nb;
-            uint32_t b = carry ? (1u << g.c) - d : d;
+            const uint32_t wd = win_width(g, w);
+            uint32_t d = raw_window(k, win_off(g, w), wd) + carry;
+            carry = d > (1u << (wd - 1));
+            uint32_t b = carry ? (1u << wd) - d : d;
             if (b) atomicAdd(&hist[w * g.nbk + b], 1u);
         }
     }
@@ -161,9 +169,10 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scal
         scalar_words(k, scalars, i);
         uint32_t carry = 0;
         for (uint32_t w = 0; w < g.nwin; w++) {
-            uint32_t d = raw_window(k, w * g.c, g.c) + carry;
-            carry = d > g.nb;
-            uint32_t b = carry ? (1u << g.c) - d : d;
+            const uint32_t wd = win_width(g, w);
+            uint32_t d = raw_window(k, win_off(g, w), wd) + carry;
+            carry = d > (1u << (wd - 1));
+            uint32_t b = carry ? (1u << wd) - d : d;
             if (b) {
                 uint32_t pos = atomicAdd(&cursor[w * g.nbk + b], 1u);
                 sorted[pos] = ((uint32_t)i << 1) | carry;     // carry == 1 <=> negative digit
@@ -172,13 +181,20 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scal
     }
 }
 
-template <class F> __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
-                                                                           MsmGeom g, uint32_t *buckets) {
+#ifndef P2B_ACC_MIN_BLOCKS
+#define P2B_ACC_MIN_BLOCKS 1
+#endif
+template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
+                                                                           MsmGeom g, uint32_t *buckets, int first) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
     const uint32_t total = g.nwin * g.nbk;
     for (uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += gridDim.x * blockDim.x) {
         const uint32_t lo = offsets[gb], hi = offsets[gb + 1];
         Xyzz<F> acc = xyzz_infinity<F>();
+        if (!first) {                                          // later chunk of a streamed MSM: continue the bucket
+            if (lo == hi) continue;
+            acc = load_xyzz<F>(buckets, gb);
+        }
 #pragma unroll 1
         for (uint32_t e = lo; e < hi; e++) {
             const uint32_t ent = __ldg(sorted + e);
@@ -293,7 +309,7 @@ template <class F> __global__ void k_msm_final(const uint32_t *wsum, MsmGeom g, 
 #pragma unroll 1
     for (int w = (int)g.nwin - 2; w >= 0; w--) {
 #pragma unroll 1
-        for (uint32_t j = 0; j < g.c; j++) acc = xdbl(acc);
+        for (uint32_t j = 0; j < win_width(g, (uint32_t)w); j++) acc = xdbl(acc);
         acc = xadd(acc, load_xyzz<F>(wsum, w));
     }
     bool inf = is_zero(acc.zz);
@@ -331,15 +347,32 @@ template <class F> __global__ void k_sum_points(const uint32_t *wire, uint32_t c
 }
 
 // ------------------------------------------------------------------------------------------------- host side
+// Window geometry.  The 255 bits (r < 2^254 plus one bit of head-room for the signed-digit carry) are split into nwin
+// windows whose widths differ by at most one bit -- a short top window would put n / 2^bits terms into each of a few
+// buckets and serialise them on a few threads (profiles/r1a/msm_c_sweep.log: 165 s at 2^26 with a 2-bit top window).
+// The narrow windows (twice the load per bucket, half the buckets) come first so that their longer threads start first.
+// Width: the widest c <= 0.55 log2(n) + 4.2 that is minimal for its window count -- a fit to the sweeps on B200
+// (2^20 -> 15, 2^22 -> 16, 2^24 and 2^26 -> 17): more windows cost n mixed adds each, wider windows leave fewer terms per
+// bucket (warp-level imbalance, one thread per bucket) and lengthen the serial strip walk of the bucket reduction.
 static inline MsmGeom msm_geometry(size_t n) {
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    MsmGeom g;
-    int c = (int)lg - 4;
-    if (c < 6) c = 6;
-    if (c > 16) c = 16;
-    g.c = (uint32_t)c;
-    g.nwin = 254 / g.c + 1;
+    int target = (int)(0.55 * lg + 4.2);
+    if (const char *e = getenv("P2B_MSM_C")) {      // tuning override (results do not depend on the geometry)
+        int v = atoi(e);
+        if (v >= 2 && v <= 22) target = v;
+    }
+    if (target < 6) target = 6;
+    if (target > 20) target = 20;
+    MsmGeom g{};
+    for (int c = target; c >= 2; c--) {
+        const uint32_t nwin = (255 + c - 1) / c;
+        if ((255 + nwin - 1) / nwin != (uint32_t)c) continue;       // fewer bits would do for this many windows
+        g.c = (uint32_t)c;
+        g.nwin = nwin;
+        break;
+    }
+    g.nnarrow = g.nwin * g.c - 255;
     g.nb = 1u << (g.c - 1);
     g.nbk = g.nb + 1;
     g.strip = g.nb > 1024 ? g.nb / 1024 : 1;
@@ -347,17 +380,22 @@ static inline MsmGeom msm_geometry(size_t n) {
     return g;
 }
 
-template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire) {
+// One MSM, or one chunk of a streamed MSM: `geom_n` (>= n) fixes the window geometry and the scratch sizes for all chunks;
+// MSM_FIRST starts fresh buckets, MSM_LAST runs the bucket / window reduction and writes the affine result.
+enum { MSM_FIRST = 1, MSM_LAST = 2 };
+template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire,
+                                 size_t geom_n, int phase, uint64_t err_base) {
     constexpr int W = FieldTraits<F>::WORDS, WU = Wire<F>::WORDS_UNCOMPRESSED;
-    if (n >= ((size_t)1 << 31)) return ctx_fail(c, P2B_EARG, "msm: n must be < 2^31");
-    MsmGeom g = msm_geometry(n ? n : 1);
+    if (geom_n >= ((size_t)1 << 31) || n > geom_n) return ctx_fail(c, P2B_EARG, "msm: chunk must be < 2^31 terms");
+    MsmGeom g = msm_geometry(geom_n ? geom_n : 1);
+    const size_t cap_n = geom_n ? geom_n : 1;
     const size_t nslots = (size_t)g.nwin * g.nbk;
     const size_t xy = (size_t)4 * W * 4;                       // bytes per XYZZ point
     int rc;
     // msm_a: affine Montgomery points ; msm_b: hist | offsets | cursor ; msm_c: sorted entries ; msm_d: buckets | s1 | s2 | wsum
-    if ((rc = dev_reserve(c, c->msm_a, (n ? n : 1) * WU * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_a, cap_n * WU * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_b, (3 * nslots + 4) * 4))) return rc;
-    if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * (n ? n : 1) * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * cap_n * 4))) return rc;
     const size_t nred = (size_t)g.nwin * g.tpw;
     if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin) * xy))) return rc;
     uint32_t *aff = (uint32_t *)c->msm_a.p;
@@ -369,21 +407,26 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
     if (grid < 1) grid = 1;
     prof_begin(c, P2B_PROF_MSM_SORT);
-    k_msm_prepare<F><<<grid, 256, 0, c->stream>>>((const uint32_t *)d_points, aff, n, c->d_err);
-    k_msm_hist<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err);
+    k_msm_prepare<F><<<grid, 256, 0, c->stream>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
+    k_msm_hist<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base);
     k_msm_scan<<<1, 1024, 0, c->stream>>>(hist, offsets, cursor, (uint32_t)nslots);
     k_msm_scatter<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, cursor, sorted);
     prof_end(c, P2B_PROF_MSM_SORT, 4);
     int agrid = (int)((nslots + 127) / 128);
     prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
-    k_msm_accumulate<F><<<agrid, 128, 0, c->stream>>>(aff, offsets, sorted, g, buckets);
+    k_msm_accumulate<F><<<agrid, 128, 0, c->stream>>>(aff, offsets, sorted, g, buckets, (phase & MSM_FIRST) != 0);
     prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
+    c->launches += 5;
+    if (!(phase & MSM_LAST)) {
+        P2B_CUDA(c, cudaGetLastError());
+        return P2B_OK;
+    }
     prof_begin(c, P2B_PROF_MSM_REDUCE);
     k_msm_reduce1<F><<<(int)((nred + 127) / 128), 128, 0, c->stream>>>(buckets, g, s1, s2);
     k_msm_reduce2<F><<<g.nwin, 256, 0, c->stream>>>(s1, s2, g, wsum);
     k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
     prof_end(c, P2B_PROF_MSM_REDUCE, 3);
-    c->launches += 8;
+    c->launches += 3;
     P2B_CUDA(c, cudaGetLastError());
     return P2B_OK;
 }

@@ -97,6 +97,12 @@ P2B_HD GlvSplit glv_decompose(const uint32_t k[8]) {
 // beta (Montgomery form) with phi(x, y) = (beta x, y) = [lambda](x, y)
 P2B_DEF_CONST(G1_BETA, {0xd782e155u, 0x71930c11u, 0xffbe3323u, 0xa6bb947cu, 0xd4741444u, 0xaa303344u, 0x26594943u, 0x2c3b3f0du})
 P2B_HD Fq g1_beta() { Fq b; for (int i = 0; i < 8; i++) b.l[i] = P2B_C(G1_BETA, i); return b; }
+// On the twist the same lambda belongs to the other cube root: (beta^2 x, y) = [lambda](x, y) for points of the order-r
+// subgroup of E'(Fq2) (tests/test_oracle.py::test_glv_constants).  beta^2 in Montgomery form:
+P2B_DEF_CONST(G2_BETA, {0x13e80b9cu, 0x3350c88eu, 0xdb5e56b9u, 0x7dce557cu, 0xb615564au, 0x6001b4b8u, 0x020217e0u, 0x2682e617u})
+P2B_HD Fq g2_beta() { Fq b; for (int i = 0; i < 8; i++) b.l[i] = P2B_C(G2_BETA, i); return b; }
+P2B_HD Fq endo_x(const Fq &x) { return mul(x, g1_beta()); }
+P2B_HD Fq2 endo_x(const Fq2 &x) { return mul_fq(x, g2_beta()); }
 
 // ------------------------------------------------------------------ table storage policies
 // One column per thread: word w of entry e lives at base[(e * WORDS2 + w) * stride].
@@ -121,6 +127,35 @@ template <class F> struct StridedTable {
         return r;
     }
 };
+
+// One column per thread in GLOBAL memory (L2 resident), 16-byte granules: granule g of entry e lives at
+// base[(e * G + g) * stride] with G = 2 * WORDS / 4, so a warp reads 512 contiguous bytes per granule.  Used for G2,
+// whose 1 KB table per thread would otherwise cap the SM at 4 warps.
+#if defined(__CUDACC__)
+template <class F> struct GlobalTable {
+    uint4 *base;
+    size_t stride;
+    static constexpr int W = FieldTraits<F>::WORDS;
+    static constexpr int G = 2 * W / 4;
+    __device__ __forceinline__ void put(int e, const F &x, const F &y) const {
+#pragma unroll
+        for (int g = 0; g < G / 2; g++) {
+            base[(size_t)(e * G + g) * stride] = make_uint4(get_word(x, 4 * g), get_word(x, 4 * g + 1), get_word(x, 4 * g + 2), get_word(x, 4 * g + 3));
+            base[(size_t)(e * G + G / 2 + g) * stride] = make_uint4(get_word(y, 4 * g), get_word(y, 4 * g + 1), get_word(y, 4 * g + 2), get_word(y, 4 * g + 3));
+        }
+    }
+    __device__ __forceinline__ Aff<F> get(int e) const {
+        Aff<F> r;
+#pragma unroll
+        for (int g = 0; g < G / 2; g++) {
+            uint4 a = base[(size_t)(e * G + g) * stride], b = base[(size_t)(e * G + G / 2 + g) * stride];
+            set_word(r.x, 4 * g, a.x); set_word(r.x, 4 * g + 1, a.y); set_word(r.x, 4 * g + 2, a.z); set_word(r.x, 4 * g + 3, a.w);
+            set_word(r.y, 4 * g, b.x); set_word(r.y, 4 * g + 1, b.y); set_word(r.y, 4 * g + 2, b.z); set_word(r.y, 4 * g + 3, b.w);
+        }
+        return r;
+    }
+};
+#endif
 
 // ------------------------------------------------------------------ odd-multiples table with one common Z
 // madd-2007-bl on a point pair known to be distinct and finite, also returning Z3/Z1 = 2H.
@@ -211,7 +246,7 @@ template <class F> P2B_HD Jac<F> mul_binary(const Aff<F> &p, const uint32_t k[8]
 
 // ------------------------------------------------------------------ G1: GLV + 2 x 33 signed windows
 // k canonical (< r).  p must be on the curve (order r) -- the caller routes anything else to mul_binary.
-template <class Tbl> P2B_HD Jac<Fq> g1_mul_glv(const Aff<Fq> &p, const uint32_t k[8], const Tbl &tbl, Fq *zr, bool &bad) {
+template <class F, class Tbl> P2B_HD Jac<F> mul_glv(const Aff<F> &p, const uint32_t k[8], const Tbl &tbl, F *zr, bool &bad) {
     GlvSplit s = glv_decompose(k);
     // make both halves odd by adding lattice vectors (a1 odd, b1 even; a2 odd, b2 odd): the represented scalar
     // k1 + k2*lambda (mod r) is unchanged.  Work on signed values: v = sign * magnitude.
@@ -246,19 +281,18 @@ template <class Tbl> P2B_HD Jac<Fq> g1_mul_glv(const Aff<Fq> &p, const uint32_t 
         for (int i = 0; i < 5; i++) { s.k1[i] = x1[i]; s.k2[i] = x2[i]; }
         (void)t;
     }
-    Fq zg = build_odd_table<Fq>(p, tbl, zr, bad);
-    const Fq beta = g1_beta();
+    F zg = build_odd_table<F>(p, tbl, zr, bad);
     uint32_t m1[4], m2[4];
     shr1<4>(m1, s.k1, s.k1[4]);
     shr1<4>(m2, s.k2, s.k2[4]);
     uint32_t top1 = s.k1[4] >> 1, top2 = s.k2[4] >> 1;   // k >> 129, must be < 8 (|k| < 2^132)
     bad |= (top1 > 7) | (top2 > 7);
     // top window: acc = T[top1] (+-) , then + phi(T[top2])
-    Aff<Fq> q = tbl.get(top1 & 7);
+    Aff<F> q = tbl.get(top1 & 7);
     q.y = cneg(q.y, s.neg1);
-    Jac<Fq> acc = jac_from_aff(q);
+    Jac<F> acc = jac_from_aff(q);
     q = tbl.get(top2 & 7);
-    q.x = mul(q.x, beta);
+    q.x = endo_x(q.x);
     q.y = cneg(q.y, s.neg2);
     acc = jac_madd(acc, q);
 #pragma unroll 1
@@ -271,13 +305,17 @@ template <class Tbl> P2B_HD Jac<Fq> g1_mul_glv(const Aff<Fq> &p, const uint32_t 
             uint32_t idx; bool negd;
             digit_from_nibble(u, idx, negd);
             q = tbl.get(idx);
-            if (h) q.x = mul(q.x, beta);
+            if (h) q.x = endo_x(q.x);
             q.y = cneg(q.y, negd != (h ? s.neg2 : s.neg1));
             acc = jac_madd(acc, q);
         }
     }
     acc.z = mul(acc.z, zg);                     // back from E'' to E
     return acc;
+}
+
+template <class Tbl> P2B_HD Jac<Fq> g1_mul_glv(const Aff<Fq> &p, const uint32_t k[8], const Tbl &tbl, Fq *zr, bool &bad) {
+    return mul_glv<Fq>(p, k, tbl, zr, bad);
 }
 
 // ------------------------------------------------------------------ G2 (and generic): 64 signed windows

@@ -9,12 +9,12 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2b.so")
+LIB_PATH = os.environ.get("P2B_LIB") or os.path.join(_HERE, "libp2b.so")   # P2B_LIB: tuning builds of the same library
 
 OK, EARG, EDECODE, EINFINITY_IN, EINFINITY_OUT, ECUDA = range(6)
 DEC_NOT_ON_CURVE, DEC_COORDINATE, DEC_UNEXPECTED_INFORMATION, DEC_UNEXPECTED_COMPRESSION_MODE = 1, 2, 3, 4
 ENC_UNCOMPRESSED, ENC_COMPRESSED, ENC_RAW_MONT_LE = 0, 1, 2
-CHECK_INPUT, REJECT_INFINITY = 1, 2
+CHECK_INPUT, REJECT_INFINITY, G2_SUBGROUP = 1, 2, 4
 G1, G2 = 0, 1
 
 # every symbol include/p2b.h declares (tests/test_abi.py checks the header and this list agree)

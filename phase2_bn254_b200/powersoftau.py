@@ -83,7 +83,8 @@ class BatchedAccumulator:
 
     @classmethod
     def transform(cls, input_map, output_map, input_is_compressed, compress_the_output,
-                  check_input_for_correctness, key, parameters, ctx=None, shard_index=0, shard_count=1):
+                  check_input_for_correctness, key, parameters, ctx=None, shard_index=0, shard_count=1,
+                  g2_in_subgroup=False):
         """Transforms the accumulator with a private key (batched_accumulator.rs:1119-1292).
 
         Writes output_map[64 : accumulator end]; bytes [0, 64) and the public key tail are the caller's, as in
@@ -97,7 +98,8 @@ class BatchedAccumulator:
         try:
             ctx.pot_transform(input_map, output_map, parameters.size, parameters.batch_size, be(key.tau),
                               be(key.alpha), be(key.beta), bool(input_is_compressed), bool(compress_the_output),
-                              bool(check_input_for_correctness), shard_index, shard_count)
+                              int(bool(check_input_for_correctness)) | (_lib.G2_SUBGROUP if g2_in_subgroup else 0),
+                              shard_index, shard_count)
         except _lib.P2BError as e:
             if e.code == _lib.EDECODE:
                 names = {1: "NotOnCurve", 2: "CoordinateDecodingError", 3: "UnexpectedInformation",

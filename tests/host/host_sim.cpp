@@ -54,6 +54,7 @@ int sim_point_mul(int g2, const uint8_t *in, const uint8_t *k_be, uint8_t *out, 
         Jac<Fq2> r;
         if (inf) r = jac_infinity<Fq2>();
         else if (path == 0 || path == 1) r = mul_window4<Fq2>(p, k, tbl, zr, bad);
+        else if (path == 3) r = mul_glv<Fq2>(p, k, tbl, zr, bad);
         else r = mul_binary<Fq2>(p, k);
         Aff<Fq2> a; bool oinf; to_affine(r, a, oinf);
         uint32_t ow[32]; point_encode<Fq2>(ow, a, oinf, out_enc);

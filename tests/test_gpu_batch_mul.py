@@ -119,3 +119,17 @@ def test_linearity_large(ctx, oracle):
     p3 = ctx.batch_mul(0, pts, be(a * b % R_MOD))
     assert np.array_equal(p2, p3)
     assert p3[:64 * 64].tobytes() == oracle.batch_mul(0, pts[:64 * 64].tobytes(), be(a * b % R_MOD), threads=8)
+
+
+def test_g2_subgroup_flag_uses_endomorphism_and_matches(ctx, oracle):
+    """P2B_G2_SUBGROUP: the opt-in endomorphism split for G2 inputs known to lie in the order-r subgroup."""
+    from phase2_bn254_b200 import lib
+    n = len(EDGE_SCALARS) + 300
+    pts = random_points(oracle, 1, n, seed=31)
+    sc = b"".join(be(k) for k in EDGE_SCALARS) + random_scalars(300, seed=32)
+    exp = oracle.batch_mul(1, pts, sc, 0, 1, threads=8)
+    assert ctx.batch_mul(1, pts, sc, 0, 1, flags=lib.G2_SUBGROUP).tobytes() == exp
+    assert ctx.batch_mul(1, pts, sc, 0, 1).tobytes() == exp
+    tau = be(0x1234567 ** 9 % R_MOD)
+    exp = oracle.batch_mul_powers(1, pts, tau, None, 5, threads=8)
+    assert ctx.batch_mul_powers(1, pts, tau, None, 5, flags=lib.G2_SUBGROUP | lib.REJECT_INFINITY).tobytes() == exp

@@ -71,3 +71,25 @@ def test_msm_rejects_bad_input(ctx, oracle):
     with pytest.raises(lib.P2BError) as e:
         ctx.msm(0, random_points(oracle, 0, 2, seed=62), be(1) + b"\xff" * 32)
     assert e.value.code == lib.EARG and e.value.index == 1
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_msm_streamed_host_path(ctx, oracle, group, monkeypatch):
+    """Host buffers above the streaming threshold are processed chunk by chunk into the same buckets (H2D overlapped
+    with the sort / accumulate of the previous chunk); the threshold is lowered through the test hook."""
+    n = 3000
+    pts = bytearray(random_points(oracle, group, n, seed=71))
+    size = 128 if group else 64
+    pts[size * 1500: size * 1501] = bytes([0x40]) + bytes(size - 1)
+    sc = random_scalars(n, seed=72)
+    exp = oracle.msm(group, bytes(pts), sc, threads=8)
+    for chunk in (700, 1000, 2999):
+        monkeypatch.setenv("P2B_MSM_STREAM_CHUNK", str(chunk))
+        assert ctx.msm(group, bytes(pts), sc) == exp
+    monkeypatch.setenv("P2B_MSM_STREAM_CHUNK", "512")
+    from phase2_bn254_b200 import lib
+    bad = bytearray(pts)
+    bad[size * 2000] |= 0x80
+    with pytest.raises(lib.P2BError) as e:
+        ctx.msm(group, bytes(bad), sc)
+    assert e.value.code == lib.EDECODE and e.value.index == 2000

@@ -100,3 +100,17 @@ def test_phase2_contribute(ctx, oracle, m, n_contrib):
     # a second contribution on top (the contributions list grows)
     exp2, h2 = oracle.phase2_contribute(exp_file, be(delta + 1), s, r, threads=8)
     assert p.contribute(delta + 1, s, r_g2=r, ctx=ctx) == h2 and p.data.tobytes() == exp2
+
+
+def test_transform_with_g2_subgroup_flag(ctx, oracle):
+    """The opt-in endomorphism path for the TauG2 / BetaG2 sections gives the same response bytes."""
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    size, batch = 6, 16
+    params = CeremonyParams(size, batch)
+    ch0 = oracle.pot_generate_initial(size)
+    ch1 = oracle.pot_transform(ch0, size, batch, be(TAU), be(ALPHA), be(BETA), out_compressed=False, threads=8)
+    exp = oracle.pot_transform(ch1, size, batch, be(BETA), be(TAU), be(ALPHA), threads=8)
+    out = np.zeros(params.contribution_size, dtype=np.uint8)
+    BatchedAccumulator.transform(np.frombuffer(ch1, dtype=np.uint8), out, False, True, False, PrivateKey(BETA, TAU, ALPHA),
+                                 params, ctx=ctx, g2_in_subgroup=True)
+    assert out[64:len(exp)].tobytes() == exp[64:]
