@@ -130,6 +130,18 @@ int p2b_pot_transform(p2b_ctx *ctx, const uint8_t *challenge, uint64_t challenge
                       uint64_t response_len, uint32_t size_log2, uint32_t batch_size, int in_compressed,
                       int out_compressed, int check_input, const uint8_t tau_be[32], const uint8_t alpha_be[32],
                       const uint8_t beta_be[32], uint32_t shard_index, uint32_t shard_count);
+/* BatchedAccumulator::decompress (powersoftau/src/batched_accumulator.rs:543-618): compressed response -> uncompressed
+ * accumulator of the next challenge.  Writes [64, accumulator_size(uncompressed)) of `challenge`; the 64-byte hash prefix
+ * stays with the caller (verify_transform_constrained.rs:207-229).  Any decoded point at infinity is an error, as in
+ * read_points_chunk (:987-991); check_input = CheckForCorrectness. */
+int p2b_pot_decompress(p2b_ctx *ctx, const uint8_t *response, uint64_t response_len, uint8_t *challenge,
+                       uint64_t challenge_len, uint32_t size_log2, int check_input, uint32_t shard_index,
+                       uint32_t shard_count);
+/* Bulk point codec (no scalar multiplication): out[i] = in[i] re-encoded.  Decompression (square roots), checked
+ * deserialisation (P2B_CHECK_INPUT = is_on_curve, ec.rs:133-148; the point reads of Parameters::read,
+ * bellman/src/groth16/mod.rs:287-383) and compression.  Same error reporting as the batch_mul entry points. */
+int p2b_g1_recode(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, int in_enc, int out_enc, int flags);
+int p2b_g2_recode(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, int in_enc, int out_enc, int flags);
 /* MPCParameters::contribute over the serialized parameters (`MPCParameters::write` format).  The RNG-derived values
  * are inputs: delta (Fr), s (G1 uncompressed, = G1::rand) and r (G2 uncompressed, = hash_to_g2(transcript) -- the
  * caller computes it from p2b_phase2_transcript).  params_out must hold params_len + 384 bytes.  Returns the

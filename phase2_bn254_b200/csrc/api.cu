@@ -171,6 +171,18 @@ static int host_batch(Ctx *c, int g2, const uint8_t *in, uint8_t *out, size_t n,
     return ctx_collect_error(c);
 }
 
+static int host_recode(Ctx *c, int g2, const uint8_t *in, uint8_t *out, size_t n, int in_enc, int out_enc, int flags) {
+    if (!in || !out) return ctx_fail(c, P2B_EARG, "null buffer");
+    HostJob j;
+    memset(&j, 0, sizeof j);
+    j.g2 = g2; j.in = in; j.out = out; j.n = n; j.in_enc = in_enc; j.out_enc = out_enc; j.flags = flags;
+    j.sc.mode = 3;
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if ((rc = run_host_job(c, j))) return rc;
+    return ctx_collect_error(c);
+}
+
 static int powers_spec(Ctx *c, ScalarSpec &sc, const uint8_t tau_be[32], const uint8_t *coeff_be, uint64_t start) {
     memset(&sc, 0, sizeof sc);
     sc.mode = 2;
@@ -243,10 +255,12 @@ static void shard_range(uint64_t count, uint32_t idx, uint32_t cnt, uint64_t &lo
     hi = lo + per + (idx < rem ? 1 : 0);
 }
 
+// recode: no scalar multiplication, the five sections are only re-encoded (BatchedAccumulator::decompress)
 static int pot_transform(Ctx *c, const uint8_t *challenge, uint64_t challenge_len, uint8_t *response, uint64_t response_len,
                          uint32_t size_log2, uint32_t batch_size, int in_c, int out_c, int check, const uint8_t *tau,
-                         const uint8_t *alpha, const uint8_t *beta, uint32_t shard_index, uint32_t shard_count) {
-    if (!challenge || !response || !tau || !alpha || !beta) return ctx_fail(c, P2B_EARG, "null argument");
+                         const uint8_t *alpha, const uint8_t *beta, uint32_t shard_index, uint32_t shard_count,
+                         bool recode = false) {
+    if (!challenge || !response || (!recode && (!tau || !alpha || !beta))) return ctx_fail(c, P2B_EARG, "null argument");
     if (size_log2 == 0 || size_log2 > 28) return ctx_fail(c, P2B_EARG, "size_log2 out of range");
     if (batch_size == 0) return ctx_fail(c, P2B_EARG, "batch_size must be positive");
     if (shard_count == 0 || shard_index >= shard_count) return ctx_fail(c, P2B_EARG, "bad shard");
@@ -275,7 +289,8 @@ static int pot_transform(Ctx *c, const uint8_t *challenge, uint64_t challenge_le
         j.in_enc = in_c ? P2B_ENC_COMPRESSED : P2B_ENC_UNCOMPRESSED;
         j.out_enc = out_c ? P2B_ENC_COMPRESSED : P2B_ENC_UNCOMPRESSED;
         j.flags = flags;
-        if ((rc = powers_spec(c, j.sc, tau, sec.coeff == 1 ? alpha : sec.coeff == 2 ? beta : nullptr, lo))) return rc;
+        if (recode) j.sc.mode = 3;
+        else if ((rc = powers_spec(c, j.sc, tau, sec.coeff == 1 ? alpha : sec.coeff == 2 ? beta : nullptr, lo))) return rc;
         if ((rc = run_host_job(c, j))) return rc;
         if ((rc = ctx_collect_error(c))) return rc;   // per section, so the index is section-relative like the reference's
         ioff += sec.count * isz;
@@ -288,8 +303,8 @@ static int pot_transform(Ctx *c, const uint8_t *challenge, uint64_t challenge_le
         j.in_enc = in_c ? P2B_ENC_COMPRESSED : P2B_ENC_UNCOMPRESSED;
         j.out_enc = out_c ? P2B_ENC_COMPRESSED : P2B_ENC_UNCOMPRESSED;
         j.flags = flags;
-        j.sc.mode = 1;
-        if (!read_scalar_be(beta, j.sc.k)) return ctx_fail(c, P2B_EARG, "beta not canonical");
+        j.sc.mode = recode ? 3 : 1;
+        if (!recode && !read_scalar_be(beta, j.sc.k)) return ctx_fail(c, P2B_EARG, "beta not canonical");
         if ((rc = run_host_job(c, j))) return rc;
         if ((rc = ctx_collect_error(c))) return rc;
     }
@@ -545,6 +560,19 @@ int p2b_pot_transform(p2b_ctx *h, const uint8_t *challenge, uint64_t challenge_l
     return h ? pot_transform(&h->c, challenge, challenge_len, response, response_len, size_log2, batch_size, in_compressed,
                              out_compressed, check_input, tau, alpha, beta, shard_index, shard_count)
              : P2B_EARG;
+}
+
+int p2b_pot_decompress(p2b_ctx *h, const uint8_t *response, uint64_t response_len, uint8_t *challenge, uint64_t challenge_len,
+                       uint32_t size_log2, int check_input, uint32_t shard_index, uint32_t shard_count) {
+    return h ? pot_transform(&h->c, response, response_len, challenge, challenge_len, size_log2, 1, 1, 0, check_input, nullptr,
+                             nullptr, nullptr, shard_index, shard_count, true)
+             : P2B_EARG;
+}
+int p2b_g1_recode(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, int ie, int oe, int fl) {
+    return h ? host_recode(&h->c, 0, in, out, n, ie, oe, fl) : P2B_EARG;
+}
+int p2b_g2_recode(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, int ie, int oe, int fl) {
+    return h ? host_recode(&h->c, 1, in, out, n, ie, oe, fl) : P2B_EARG;
 }
 
 int p2b_phase2_transcript(p2b_ctx *h, const uint8_t *params, uint64_t params_len, const uint8_t delta[32], const uint8_t s[64],

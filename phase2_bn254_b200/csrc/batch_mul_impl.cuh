@@ -104,6 +104,36 @@ template <class F> __global__ void __launch_bounds__(128) k_decompress(Decompres
     }
 }
 
+// ------------------------------------------------------------------------------------------------- bulk codec
+// out[i] = re-encoding of in[i]: decompression (sqrt), checked deserialisation (is_on_curve) and compression without any
+// scalar multiplication -- BatchedAccumulator::decompress (batched_accumulator.rs:543-618) and the checked point reads of
+// Parameters::read (bellman/src/groth16/mod.rs:287-383).
+struct RecodeParams {
+    const uint32_t *in;
+    uint32_t *out;
+    size_t n;
+    int in_enc, out_enc, flags;
+    unsigned long long *err;
+    uint64_t err_base;
+};
+template <class F> __global__ void __launch_bounds__(128) k_recode(RecodeParams p) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, WC = Wire<F>::WORDS_COMPRESSED;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[WU];
+        if (p.in_enc == ENC_COMPRESSED) load_words<WC>(w, p.in + i * WC);
+        else load_words<WU>(w, p.in + i * WU);
+        Aff<F> a;
+        bool inf;
+        int rc = point_decode<F>(a, inf, w, p.in_enc, (p.flags & P2B_CHECK_INPUT) != 0);
+        if (rc) { report(p.err, p.err_base + i, P2B_EDECODE, rc); inf = true; }
+        else if (inf && (p.flags & P2B_REJECT_INFINITY)) report(p.err, p.err_base + i, P2B_EINFINITY_IN, 0);
+        uint32_t o[WU];
+        point_encode<F>(o, a, inf, p.out_enc);
+        if (p.out_enc == ENC_COMPRESSED) store_words<WC>(p.out + i * WC, o);
+        else store_words<WU>(p.out + i * WU, o);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------- the hot kernel
 struct BatchMulParams {
     const uint32_t *in;
@@ -261,6 +291,15 @@ template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_i
     constexpr bool IS_G2 = W == 16;
     const size_t elem = (size_t)W * 4;
     int rc;
+    if (sc.mode == 3) {                      // codec only
+        RecodeParams rp{(const uint32_t *)d_in, (uint32_t *)d_out, n, in_enc, out_enc, flags, c->d_err, err_base};
+        int blocks = (int)((n + 127) / 128);
+        if (blocks > c->sm_count * 12) blocks = c->sm_count * 12;
+        k_recode<F><<<blocks, 128, 0, c->stream>>>(rp);
+        c->launches++;
+        P2B_CUDA(c, cudaGetLastError());
+        return P2B_OK;
+    }
     if ((rc = dev_reserve(c, c->jac, 3 * n * elem))) return rc;
     if ((rc = dev_reserve(c, c->prefix, n * elem))) return rc;
     uint32_t *jx = (uint32_t *)c->jac.p, *jy = jx + n * W, *jz = jy + n * W;
@@ -297,6 +336,8 @@ template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_i
     static bool attr_set = false;
     if (!attr_set && smem) {
         P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     size_t ntiles = (n + BLOCK - 1) / BLOCK;

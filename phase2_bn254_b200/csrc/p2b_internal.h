@@ -65,7 +65,7 @@ void prof_end(Ctx *c, int slot, int kernels);
 
 // ---- batch_mul.cu ----
 struct ScalarSpec {
-    int mode;                     // 0 = array (device, 32 B BE each), 1 = broadcast, 2 = powers of tau
+    int mode;                     // 0 = array (device, 32 B BE each), 1 = broadcast, 2 = powers of tau, 3 = none (codec only)
     const void *d_scalars;        // mode 0
     uint32_t k[8];                // mode 1: canonical little-endian limbs
     uint32_t tau[8], coeff[8];    // mode 2: canonical limbs (coeff = 1 when absent)

@@ -26,6 +26,7 @@ SYMBOLS = [
     "p2b_pot_accumulator_size", "p2b_pot_transform", "p2b_phase2_transcript", "p2b_phase2_contribute",
     "p2b_g1_msm", "p2b_g2_msm", "p2b_g1_msm_dev", "p2b_g2_msm_dev", "p2b_g1_sum_points", "p2b_g2_sum_points",
     "p2b_fr_fft", "p2b_fr_fft_dev", "p2b_profile_enable", "p2b_profile_read",
+    "p2b_pot_decompress", "p2b_g1_recode", "p2b_g2_recode",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -82,6 +83,9 @@ def load():
     if hasattr(lib, "p2b_fr_fft"):
         lib.p2b_fr_fft.argtypes = [vp, u8p, u32, i32, i32]
         lib.p2b_fr_fft_dev.argtypes = [vp, vp, u32, i32, i32]
+    lib.p2b_pot_decompress.argtypes = [vp, u8p, u64, u8p, u64, u32, i32, u32, u32]
+    lib.p2b_g1_recode.argtypes = [vp, u8p, u8p, sz, i32, i32, i32]
+    lib.p2b_g2_recode.argtypes = [vp, u8p, u8p, sz, i32, i32, i32]
     lib.p2b_profile_enable.argtypes = [vp, i32]
     lib.p2b_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     _lib = lib
@@ -178,6 +182,22 @@ class Context:
         self._check(fn(self.h, _ptr(pts), _ptr(out), n, _ptr(t), _ptr(cf) if cf is not None else None, start, in_enc,
                        out_enc, flags))
         return out[: n * enc_size(group, out_enc)]
+
+    def recode(self, group, points, in_enc, out_enc, flags=0, out=None):
+        """Bulk codec: decompress / compress / checked deserialisation without a scalar multiplication."""
+        pts = _host(points)
+        n = pts.size // enc_size(group, in_enc)
+        if out is None:
+            out = np.empty(max(1, n * enc_size(group, out_enc)), dtype=np.uint8)
+        fn = self.lib.p2b_g2_recode if group == G2 else self.lib.p2b_g1_recode
+        self._check(fn(self.h, _ptr(pts), _ptr(out), n, in_enc, out_enc, flags))
+        return out[: n * enc_size(group, out_enc)]
+
+    def pot_decompress(self, response, challenge, size_log2, check_input=False, shard_index=0, shard_count=1):
+        rs, ch = _host(response), challenge
+        assert isinstance(ch, np.ndarray) and ch.dtype == np.uint8 and ch.flags.writeable
+        self._check(self.lib.p2b_pot_decompress(self.h, _ptr(rs), rs.size, _ptr(ch), ch.size, size_log2, int(check_input),
+                                                shard_index, shard_count))
 
     # -- level 1 (device pointers; asynchronous until sync())
     def batch_mul_dev(self, group, d_in, d_out, n, scalars, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0):

@@ -82,6 +82,30 @@ class BatchedAccumulator:
         return cls._ctx
 
     @classmethod
+    def decompress(cls, input_map, output_map, check_input_for_correctness, parameters, ctx=None, shard_index=0,
+                   shard_count=1):
+        """Compressed response -> uncompressed accumulator (batched_accumulator.rs:543-618).  Writes
+        output_map[64 : accumulator_size]; the hash prefix is the caller's (verify_transform_constrained.rs:207-229)."""
+        ctx = ctx or cls.context()
+        try:
+            ctx.pot_decompress(input_map, output_map, parameters.size, bool(check_input_for_correctness), shard_index,
+                               shard_count)
+        except _lib.P2BError as e:
+            cls._raise(e)
+
+    @staticmethod
+    def _raise(e):
+        if e.code == _lib.EDECODE:
+            names = {1: "NotOnCurve", 2: "CoordinateDecodingError", 3: "UnexpectedInformation",
+                     4: "UnexpectedCompressionMode"}
+            raise DeserializationError("DecodingError", "%s at element %d" % (names.get(e.sub, "?"), e.index))
+        if e.code == _lib.EINFINITY_IN:
+            raise DeserializationError("PointAtInfinity", "at element %d" % e.index)
+        if e.code == _lib.EINFINITY_OUT:
+            raise AssertionError("your contribution happened to produce a point at infinity, please re-run")
+        raise e
+
+    @classmethod
     def transform(cls, input_map, output_map, input_is_compressed, compress_the_output,
                   check_input_for_correctness, key, parameters, ctx=None, shard_index=0, shard_count=1,
                   g2_in_subgroup=False):
@@ -110,3 +134,19 @@ class BatchedAccumulator:
             if e.code == _lib.EINFINITY_OUT:
                 raise AssertionError("your contribution happened to produce a point at infinity, please re-run")
             raise
+
+
+def merge_pairs(ctx, group, v1, v2, scalars):
+    """(sum r_i v1_i, sum r_i v2_i): the random linear combination behind every same_ratio check of the verifier
+    (powersoftau/src/utils.rs:112-130, phase2/src/utils.rs:59-105); two Pippenger MSMs on the GPU.  The reference draws
+    the r_i from thread_rng; here they are explicit (32-byte big-endian each).  Returns two uncompressed points."""
+    return ctx.msm(group, v1, scalars), ctx.msm(group, v2, scalars)
+
+
+def power_pairs(ctx, group, v, scalars):
+    """merge_pairs(v[..n-1], v[1..]) (utils.rs:133-135): checks that consecutive elements have the same ratio."""
+    size = 128 if group else 64
+    a = np.frombuffer(v, dtype=np.uint8) if not isinstance(v, np.ndarray) else v
+    n = a.size // size
+    sc = np.frombuffer(scalars, dtype=np.uint8) if not isinstance(scalars, np.ndarray) else scalars
+    return merge_pairs(ctx, group, a[: (n - 1) * size], a[size:], sc[: (n - 1) * 32])

@@ -93,3 +93,21 @@ def test_msm_streamed_host_path(ctx, oracle, group, monkeypatch):
     with pytest.raises(lib.P2BError) as e:
         ctx.msm(group, bytes(bad), sc)
     assert e.value.code == lib.EDECODE and e.value.index == 2000
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_power_pairs(ctx, oracle, group):
+    """The verifier's random linear combination (utils.rs:112-135) as two MSMs; same_ratio then holds for a geometric
+    progression: b == [tau] a."""
+    from phase2_bn254_b200.powersoftau import power_pairs
+    from util import G1_GEN, G2_GEN
+    n = 257
+    tau = be(0x1234567 ** 9 % R_MOD)
+    gen = G2_GEN if group else G1_GEN
+    v = oracle.batch_mul_powers(group, gen * n, tau, None, 0, threads=8)     # tau^i G
+    sc = random_scalars(n - 1, seed=91)
+    a, b = power_pairs(ctx, group, v, sc)
+    size = 128 if group else 64
+    assert a == oracle.msm(group, v[: (n - 1) * size], sc, threads=8)
+    assert b == oracle.msm(group, v[size:], sc, threads=8)
+    assert b == oracle.point_mul(group, a, tau)

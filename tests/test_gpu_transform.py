@@ -114,3 +114,57 @@ def test_transform_with_g2_subgroup_flag(ctx, oracle):
     BatchedAccumulator.transform(np.frombuffer(ch1, dtype=np.uint8), out, False, True, False, PrivateKey(BETA, TAU, ALPHA),
                                  params, ctx=ctx, g2_in_subgroup=True)
     assert out[64:len(exp)].tobytes() == exp[64:]
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_bulk_codec(ctx, oracle, group):
+    """p2b_g{1,2}_recode: compress / decompress / checked deserialisation without a scalar multiplication."""
+    from phase2_bn254_b200 import lib
+    size = 128 if group else 64
+    n = 500
+    pts = bytearray(random_points(oracle, group, n, seed=81))
+    pts[size * 7: size * 8] = bytes([0x40]) + bytes(size - 1)           # infinity is a valid encoding
+    pts = bytes(pts)
+    comp = oracle.batch_mul(group, pts, be(1), 0, 1, threads=8)
+    assert ctx.recode(group, pts, 0, 1).tobytes() == comp
+    assert ctx.recode(group, comp, 1, 0, lib.CHECK_INPUT).tobytes() == pts
+    assert ctx.recode(group, comp, 1, 1).tobytes() == comp
+    assert ctx.recode(group, pts, 0, 0, lib.CHECK_INPUT).tobytes() == pts
+    with pytest.raises(lib.P2BError) as e:
+        ctx.recode(group, pts, 0, 1, lib.REJECT_INFINITY)
+    assert e.value.code == lib.EINFINITY_IN and e.value.index == 7
+    bad = bytearray(pts); bad[size * 11 + size - 1] ^= 1
+    with pytest.raises(lib.P2BError) as e:
+        ctx.recode(group, bytes(bad), 0, 1, lib.CHECK_INPUT)
+    assert e.value.code == lib.EDECODE and e.value.sub == lib.DEC_NOT_ON_CURVE and e.value.index == 11
+    assert ctx.recode(group, bytes(bad), 0, 0).tobytes() == bytes(bad)   # unchecked accepts, like into_affine_unchecked
+    # a compressed x with no square root
+    x = bytearray(comp[: size // 2])
+    for t in range(1, 50):
+        x[-1] = (x[-1] + t) & 0xff
+        try:
+            oracle.point_recode(group, bytes(x), 1, 0)
+        except oracle.OracleError:
+            break
+    with pytest.raises(lib.P2BError) as e:
+        ctx.recode(group, bytes(x), 1, 0)
+    assert e.value.code == lib.EDECODE and e.value.sub == lib.DEC_NOT_ON_CURVE
+
+
+def test_pot_decompress(ctx, oracle):
+    """BatchedAccumulator::decompress: compressed response -> next challenge, two shards, vs the oracle."""
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, DeserializationError
+    size, batch = 5, 8
+    params = CeremonyParams(size, batch)
+    ch0 = oracle.pot_generate_initial(size)
+    resp = oracle.pot_transform(ch0, size, batch, be(TAU), be(ALPHA), be(BETA), threads=8)            # compressed
+    nxt = oracle.pot_transform(ch0, size, batch, be(TAU), be(ALPHA), be(BETA), out_compressed=False, threads=8)
+    out = np.zeros(params.accumulator_size, dtype=np.uint8)
+    for shard in range(2):
+        BatchedAccumulator.decompress(np.frombuffer(resp, dtype=np.uint8), out, True, params, ctx=ctx, shard_index=shard,
+                                      shard_count=2)
+    assert out[64:].tobytes() == nxt[64:]
+    bad = bytearray(resp)
+    bad[64 + 32 * 3] = 0x40                                             # infinity flag with stray bits
+    with pytest.raises(DeserializationError):
+        BatchedAccumulator.decompress(np.frombuffer(bytes(bad), dtype=np.uint8), out, False, params, ctx=ctx)
