@@ -170,6 +170,22 @@ int p2b_g2_sum_points(p2b_ctx *ctx, const uint8_t *points, size_t count, uint8_t
 int p2b_fr_fft(p2b_ctx *ctx, uint8_t *data, uint32_t log_n, int inverse, int coset);
 int p2b_fr_fft_dev(p2b_ctx *ctx, void *d_data, uint32_t log_n, int inverse, int coset);
 
+/* ---- group-element FFT and prepare_phase2 ---- */
+/* EvaluationDomain<E, Point<G>>::{fft, ifft} (bellman/src/domain.rs:154-174, group.rs:30-50): radix-2 transform over
+ * 2^log_d POINTS, natural order in and out; inverse => omega^-1 and x d^-1.  Infinity is a valid element. */
+int p2b_g1_group_fft(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc,
+                     int flags);
+int p2b_g2_group_fft(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc,
+                     int flags);
+/* One iteration of powersoftau/src/bin/prepare_phase2.rs:62-241: from an accumulator (challenge layout, uncompressed, or
+ * response layout, compressed; the 64-byte hash prefix included) to the image of the file phase1radix2m{m}:
+ * alpha_g1 | beta_g1 | beta_g2 | coeffs_g1[d] | coeffs_g2[d] | alpha_coeffs_g1[d] | beta_coeffs_g1[d] | h[d-1], all
+ * uncompressed, d = 2^m (reader: phase2/src/parameters.rs:182-217).  p2b_pot_radix_file_size(m) = 192 + 384 d bytes.
+ * check_input = CheckForCorrectness of the deserialisation (the binary uses Yes); flags: 0 or P2B_G2_SUBGROUP. */
+uint64_t p2b_pot_radix_file_size(uint32_t m);
+int p2b_pot_prepare_phase2(p2b_ctx *ctx, const uint8_t *accumulator, uint64_t accumulator_len, uint32_t size_log2,
+                           int compressed_input, int check_input, uint32_t m, uint8_t *out, uint64_t out_len, int flags);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -173,6 +173,20 @@ static Fr host_root_of_unity() {
     return pow_limbs(host_fr_from_u64(7), e);
 }
 
+// omega_(2^log_n) (or its inverse) in Montgomery form and the canonical limbs of n^-1 (1 for the forward transform)
+void host_domain_constants(uint32_t log_n, int inverse, uint32_t omega_mont[8], uint32_t ninv_canon[8]) {
+    Fr omega = host_root_of_unity();
+    for (uint32_t i = log_n; i < 28; i++) omega = sqr(omega);
+    Fr scale = fp_zero<FrP>();
+    scale.l[0] = 1;
+    if (inverse) {
+        omega = inv(omega);
+        scale = from_mont(inv(host_fr_from_u64((uint64_t)1 << log_n)));
+    }
+    memcpy(omega_mont, omega.l, 32);
+    memcpy(ninv_canon, scale.l, 32);
+}
+
 struct FftPlan {
     uint32_t npass, r[4], log_te;
 };

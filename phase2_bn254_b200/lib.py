@@ -27,6 +27,7 @@ SYMBOLS = [
     "p2b_g1_msm", "p2b_g2_msm", "p2b_g1_msm_dev", "p2b_g2_msm_dev", "p2b_g1_sum_points", "p2b_g2_sum_points",
     "p2b_fr_fft", "p2b_fr_fft_dev", "p2b_profile_enable", "p2b_profile_read",
     "p2b_pot_decompress", "p2b_g1_recode", "p2b_g2_recode",
+    "p2b_g1_group_fft", "p2b_g2_group_fft", "p2b_pot_radix_file_size", "p2b_pot_prepare_phase2",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -86,6 +87,11 @@ def load():
     lib.p2b_pot_decompress.argtypes = [vp, u8p, u64, u8p, u64, u32, i32, u32, u32]
     lib.p2b_g1_recode.argtypes = [vp, u8p, u8p, sz, i32, i32, i32]
     lib.p2b_g2_recode.argtypes = [vp, u8p, u8p, sz, i32, i32, i32]
+    lib.p2b_g1_group_fft.argtypes = [vp, u8p, u8p, u32, i32, i32, i32, i32]
+    lib.p2b_g2_group_fft.argtypes = [vp, u8p, u8p, u32, i32, i32, i32, i32]
+    lib.p2b_pot_radix_file_size.argtypes = [u32]
+    lib.p2b_pot_radix_file_size.restype = u64
+    lib.p2b_pot_prepare_phase2.argtypes = [vp, u8p, u64, u32, i32, i32, u32, u8p, u64, i32]
     lib.p2b_profile_enable.argtypes = [vp, i32]
     lib.p2b_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     _lib = lib
@@ -265,6 +271,26 @@ class Context:
         fn = self.lib.p2b_g2_sum_points if group == G2 else self.lib.p2b_g1_sum_points
         self._check(fn(self.h, _ptr(p), count, _ptr(out)))
         return out.tobytes()
+
+    # -- group-element FFT / prepare_phase2
+    def group_fft(self, group, points, inverse=False, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0):
+        pts = _host(points)
+        d = pts.size // enc_size(group, in_enc)
+        log_d = d.bit_length() - 1
+        if d == 0 or (1 << log_d) != d:
+            raise P2BError(EARG, "fft length must be a power of two")
+        out = np.empty(d * enc_size(group, out_enc), dtype=np.uint8)
+        fn = self.lib.p2b_g2_group_fft if group == G2 else self.lib.p2b_g1_group_fft
+        self._check(fn(self.h, _ptr(pts), _ptr(out), log_d, int(inverse), in_enc, out_enc, flags))
+        return out
+
+    def pot_prepare_phase2(self, accumulator, size_log2, m, compressed_input=False, check_input=True, flags=0):
+        """Image of the file phase1radix2m{m} (powersoftau/src/bin/prepare_phase2.rs:62-241)."""
+        acc = _host(accumulator)
+        out = np.empty(self.lib.p2b_pot_radix_file_size(m), dtype=np.uint8)
+        self._check(self.lib.p2b_pot_prepare_phase2(self.h, _ptr(acc), acc.size, size_log2, int(compressed_input),
+                                                    int(check_input), m, _ptr(out), out.size, flags))
+        return out
 
     # -- FFT
     def fr_fft(self, data, inverse=False, coset=False):
