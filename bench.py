@@ -428,6 +428,19 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
                                             "response_body_blake2b": hashlib.blake2b(rsn[64:end].tobytes()).hexdigest()[:32]}
         if size == 10:
             out["_pot10"] = (chn.tobytes(), key, rsn[64:end].tobytes())
+        if size == 20:
+            # -- next row: prepare_phase2 for m = 16 from that compressed response: 3 G1 + 1 G2 group iFFTs
+            #    of 2^16 points (d/2 log d scalar multiplications each) + the H query
+            from phase2_bn254_b200.powersoftau import prepare_phase2
+            times = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                img = prepare_phase2(ctx, rsn[:end], prm, 16, input_is_compressed=True)
+                times.append(time.perf_counter() - t0)
+            out["prepare_phase2_m16"] = {"wall_s": round(min(times), 4), "file_bytes": int(img.size),
+                                         "scalar_muls": 4 * (1 << 15) * 15 + 4 * (1 << 16),
+                                         "file_blake2b": hashlib.blake2b(img.tobytes()).hexdigest()[:32]}
         del ch, rs
     # -- config 4: Fr FFT / iFFT at 2^24, round trip bit-exact
     lf = 24

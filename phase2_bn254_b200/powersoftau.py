@@ -150,3 +150,16 @@ def power_pairs(ctx, group, v, scalars):
     n = a.size // size
     sc = np.frombuffer(scalars, dtype=np.uint8) if not isinstance(scalars, np.ndarray) else scalars
     return merge_pairs(ctx, group, a[: (n - 1) * size], a[size:], sc[: (n - 1) * 32])
+
+
+def prepare_phase2(ctx, accumulator_map, parameters, m, input_is_compressed=True, check_input_for_correctness=True,
+                   g2_in_subgroup=False):
+    """One iteration of powersoftau/src/bin/prepare_phase2.rs:62-241: the bytes of the file `phase1radix2m{m}` --
+    alpha_g1, beta_g1, beta_g2, then the Lagrange coefficients (group iFFT of the first 2^m powers) in G1, G2, alpha*G1,
+    beta*G1 and the H query tau^(i+d) G - tau^i G, all uncompressed.  `accumulator_map` is a response (compressed, the
+    binary's input) or a challenge (uncompressed) including its 64-byte hash prefix."""
+    try:
+        return ctx.pot_prepare_phase2(accumulator_map, parameters.size, m, bool(input_is_compressed),
+                                      bool(check_input_for_correctness), _lib.G2_SUBGROUP if g2_in_subgroup else 0)
+    except _lib.P2BError as e:
+        BatchedAccumulator._raise(e)
