@@ -36,7 +36,7 @@ static size_t msm_stream_chunk() {       // P2B_MSM_STREAM_CHUNK=<terms>: test h
 }
 static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
     const size_t ov = msm_stream_chunk();
-    const size_t psz = g2 ? 128 : 64, chunk = ov ? ov : MSM_STREAM_CHUNK, nchunks = (n + chunk - 1) / chunk;
+    const size_t psz = g2 ? 128 : 64, chunk = ov ? ov : MSM_STREAM_CHUNK;
     int rc;
     for (int b = 0; b < 2; b++)
         if ((rc = dev_reserve(c, c->stage_in[b], chunk * (psz + 32)))) return rc;
@@ -44,19 +44,24 @@ static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_
     uint32_t *d_out = (uint32_t *)c->misc.p;
     cudaEvent_t *ev_in = c->ev, *ev_done = c->ev + 2;
     P2B_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    for (size_t ci = 0; ci < nchunks; ci++) {
+    // the first chunks are short (1/4, 1/4, 1/2 of a chunk) so that the GPU starts working after a quarter-chunk copy
+    size_t off = 0;
+    for (size_t ci = 0; off < n; ci++) {
         const int b = (int)(ci & 1);
-        const size_t off = ci * chunk, m = off + chunk <= n ? chunk : n - off;
+        size_t m = ci < 2 ? chunk / 4 : ci == 2 ? chunk / 2 : chunk;
+        if (m == 0) m = 1;
+        if (m > n - off) m = n - off;
         P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, ci >= 2 ? ev_done[b] : c->ev[6], 0));
         char *d_pts = (char *)c->stage_in[b].p, *d_sc = d_pts + chunk * psz;
         P2B_CUDA(c, cudaMemcpyAsync(d_pts, points + off * psz, m * psz, cudaMemcpyHostToDevice, c->copy_in));
         P2B_CUDA(c, cudaMemcpyAsync(d_sc, scalars + off * 32, m * 32, cudaMemcpyHostToDevice, c->copy_in));
         P2B_CUDA(c, cudaEventRecord(ev_in[b], c->copy_in));
         P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
-        const int phase = (ci == 0 ? MSM_FIRST : 0) | (ci + 1 == nchunks ? MSM_LAST : 0);
+        const int phase = (ci == 0 ? MSM_FIRST : 0) | (off + m == n ? MSM_LAST : 0);
         rc = g2 ? msm_typed_g2(c, d_pts, d_sc, m, d_out, chunk, phase, off) : msm_typed<Fq>(c, d_pts, d_sc, m, d_out, chunk, phase, off);
         if (rc) return rc;
         P2B_CUDA(c, cudaEventRecord(ev_done[b], c->stream));
+        off += m;
     }
     P2B_CUDA(c, cudaMemcpyAsync(out, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
     return ctx_collect_error(c);

@@ -133,3 +133,27 @@ def test_g2_subgroup_flag_uses_endomorphism_and_matches(ctx, oracle):
     tau = be(0x1234567 ** 9 % R_MOD)
     exp = oracle.batch_mul_powers(1, pts, tau, None, 5, threads=8)
     assert ctx.batch_mul_powers(1, pts, tau, None, 5, flags=lib.G2_SUBGROUP | lib.REJECT_INFINITY).tobytes() == exp
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_empty_and_ragged_sizes(ctx, oracle, group):
+    """n = 0 is a no-op everywhere; sizes around the block / warp / chunk boundaries."""
+    assert ctx.batch_mul(group, b"", be(5)).size == 0
+    assert ctx.batch_mul_powers(group, b"", be(7)).size == 0
+    assert ctx.recode(group, b"", 0, 1).size == 0
+    for n in (33, 127, 129, 257, 513):
+        pts = random_points(oracle, group, n, seed=500 + n)
+        sc = random_scalars(n, seed=600 + n)
+        assert ctx.batch_mul(group, pts, sc, 0, 1).tobytes() == oracle.batch_mul(group, pts, sc, 0, 1, threads=8)
+
+
+def test_non_canonical_scalar_is_rejected(ctx, oracle):
+    from phase2_bn254_b200 import lib
+    pts = random_points(oracle, 0, 4, seed=1)
+    with pytest.raises(lib.P2BError) as e:
+        ctx.batch_mul(0, pts, be(1) * 2 + be(R_MOD) + be(1))
+    assert e.value.code == lib.EARG and e.value.index == 2
+    with pytest.raises(lib.P2BError):
+        ctx.batch_mul(0, pts, be(R_MOD))
+    with pytest.raises(lib.P2BError):
+        ctx.batch_mul(0, pts, be(1) * 3)              # n_scalars must be 1 or n
