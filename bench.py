@@ -280,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
         return
 
     acc_ms, acc_k = prof["accumulate"]
-    acc_avg_ms = acc_ms / max(1, acc_k)
+    acc_avg_ms = acc_ms / max(1, args.steps)       # the accumulation of one MSM (one launch per window group)
     achieved = 96.0 * n / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms else None
     traffic = None
     try:
@@ -301,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fq>", "achieved": round(achieved, 2) if achieved else None,
                      "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 5) if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 96 * n,
-                     "kernel_ms": round(acc_avg_ms, 4),
+                     "kernel_ms": round(acc_avg_ms, 4), "launches_per_step": int(acc_k // max(1, args.steps)),
                      "note": "integer-ALU bound (IMAD), not HBM bound: see DESIGN.md; share of step = %.2f" %
                              (acc_avg_ms / dev_ms if dev_ms else 0)},
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},

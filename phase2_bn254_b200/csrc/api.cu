@@ -37,7 +37,7 @@ int dev_reserve(Ctx *c, DevBuf &b, size_t bytes) {
     b.cap = cap;
     return P2B_OK;
 }
-void prof_begin(Ctx *c, int slot) {
+void prof_begin(Ctx *c, int slot, cudaStream_t stream) {
     if (!c->prof) return;
     Ctx::ProfSlot &s = c->prof_slot[slot];
     if (s.used == s.ev.size()) {
@@ -45,13 +45,13 @@ void prof_begin(Ctx *c, int slot) {
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
         s.ev.emplace_back(a, b);
     }
-    cudaEventRecord(s.ev[s.used].first, c->stream);
+    cudaEventRecord(s.ev[s.used].first, stream ? stream : c->stream);
 }
-void prof_end(Ctx *c, int slot, int kernels) {
+void prof_end(Ctx *c, int slot, int kernels, cudaStream_t stream) {
     if (!c->prof) return;
     Ctx::ProfSlot &s = c->prof_slot[slot];
     if (s.used >= s.ev.size()) return;
-    cudaEventRecord(s.ev[s.used].second, c->stream);
+    cudaEventRecord(s.ev[s.used].second, stream ? stream : c->stream);
     s.used++;
     s.kernels += (uint64_t)kernels;
 }
@@ -456,9 +456,11 @@ int p2b_init(int device, p2b_ctx **out) {
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&c->sort_stream, cudaStreamNonBlocking, -1) == cudaSuccess &&
               cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMallocHost(&c->h_err, sizeof(unsigned long long)) == cudaSuccess;
     for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&c->msm_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream) == cudaSuccess;
     if (!ok) { p2b_destroy(h); return P2B_ECUDA; }
     *out = h;
@@ -478,6 +480,8 @@ void p2b_destroy(p2b_ctx *h) {
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; i++) if (c->msm_ev[i]) cudaEventDestroy(c->msm_ev[i]);
+    if (c->sort_stream) cudaStreamDestroy(c->sort_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);

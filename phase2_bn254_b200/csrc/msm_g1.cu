@@ -25,10 +25,10 @@ static int msm_begin(Ctx *c) {
     return P2B_OK;
 }
 
-// Host buffers larger than STREAM_MIN terms are streamed: chunks of STREAM_CHUNK terms are copied on the H2D stream into
+// Host buffers larger than STREAM_MIN terms are streamed: chunks of up to STREAM_CHUNK terms are copied on the H2D stream into
 // a double-buffered staging area while the previous chunk is sorted and accumulated into the SAME buckets; the bucket
 // reduction runs once at the end.  The sum is unchanged (bucket contents are sums of the same terms).
-static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 24;
+static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 25;
 static size_t msm_stream_chunk() {       // P2B_MSM_STREAM_CHUNK=<terms>: test hook to exercise the streamed path at small sizes
     const char *e = getenv("P2B_MSM_STREAM_CHUNK");
     long v = e ? atol(e) : 0;
@@ -44,12 +44,13 @@ static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_
     uint32_t *d_out = (uint32_t *)c->misc.p;
     cudaEvent_t *ev_in = c->ev, *ev_done = c->ev + 2;
     P2B_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    // the first chunks are short (1/4, 1/4, 1/2 of a chunk) so that the GPU starts working after a quarter-chunk copy
-    size_t off = 0;
+    // chunk sizes double from 1/8 of the maximum (1/8, 1/8, 1/4, 1/2, 1, 1, ..): the GPU starts after a short copy, and
+    // every later copy is hidden behind the work on the terms already on the device
+    size_t off = 0, next = chunk / 8 ? chunk / 8 : 1;
     for (size_t ci = 0; off < n; ci++) {
         const int b = (int)(ci & 1);
-        size_t m = ci < 2 ? chunk / 4 : ci == 2 ? chunk / 2 : chunk;
-        if (m == 0) m = 1;
+        size_t m = next;
+        if (ci >= 1 && next < chunk) next = next * 2 < chunk ? next * 2 : chunk;
         if (m > n - off) m = n - off;
         P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, ci >= 2 ? ev_done[b] : c->ev[6], 0));
         char *d_pts = (char *)c->stage_in[b].p, *d_sc = d_pts + chunk * psz;

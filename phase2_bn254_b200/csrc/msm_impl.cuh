@@ -124,27 +124,28 @@ template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const ui
     }
 }
 
-static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *hist, unsigned long long *err, uint64_t err_base) {
+static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *hist, unsigned long long *err, uint64_t err_base,
+                                                             uint32_t w_lo, uint32_t w_hi) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t k[8];
         scalar_words(k, scalars, i);
         Fr kc;
 #pragma unroll
         for (int j = 0; j < 8; j++) kc.l[j] = k[j];
-        if (!is_canonical(kc)) report_err(err, err_base + i, P2B_EARG, 0);
+        if (w_lo == 0 && !is_canonical(kc)) report_err(err, err_base + i, P2B_EARG, 0);
         uint32_t carry = 0;
-        for (uint32_t w = 0; w < g.nwin; w++) {
+        for (uint32_t w = 0; w < w_hi; w++) {                  // the signed-digit carry needs the windows below w_lo too
             const uint32_t wd = win_width(g, w);
             uint32_t d = raw_window(k, win_off(g, w), wd) + carry;
             carry = d > (1u << (wd - 1));
             uint32_t b = carry ? (1u << wd) - d : d;
-            if (b) atomicAdd(&hist[w * g.nbk + b], 1u);
+            if (b && w >= w_lo) atomicAdd(&hist[w * g.nbk + b], 1u);
         }
     }
 }
 
 // single block: exclusive scan of `count` entries; also copies the offsets into `cursor`
-static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t count) {
+static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t count, uint32_t base) {
     __shared__ uint32_t sums[1024];
     const uint32_t t = threadIdx.x, per = (count + 1023) / 1024;
     const uint32_t lo = t * per, hi = lo + per < count ? lo + per : count;
@@ -158,22 +159,23 @@ static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *hist, 
         sums[t] += v;
         __syncthreads();
     }
-    uint32_t run = t ? sums[t - 1] : 0;
+    uint32_t run = base + (t ? sums[t - 1] : 0);
     for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; cursor[i] = run; run += hist[i]; }
-    if (t == 1023) offsets[count] = sums[1023];
+    if (t == 1023) offsets[count] = base + sums[1023];
 }
 
-static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *cursor, uint32_t *sorted) {
+static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *cursor, uint32_t *sorted,
+                                                                uint32_t w_lo, uint32_t w_hi) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t k[8];
         scalar_words(k, scalars, i);
         uint32_t carry = 0;
-        for (uint32_t w = 0; w < g.nwin; w++) {
+        for (uint32_t w = 0; w < w_hi; w++) {
             const uint32_t wd = win_width(g, w);
             uint32_t d = raw_window(k, win_off(g, w), wd) + carry;
             carry = d > (1u << (wd - 1));
             uint32_t b = carry ? (1u << wd) - d : d;
-            if (b) {
+            if (b && w >= w_lo) {
                 uint32_t pos = atomicAdd(&cursor[w * g.nbk + b], 1u);
                 sorted[pos] = ((uint32_t)i << 1) | carry;     // carry == 1 <=> negative digit
             }
@@ -185,11 +187,13 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scal
 #define P2B_ACC_MIN_BLOCKS 1
 #endif
 template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
-                                                                           MsmGeom g, uint32_t *buckets, int first) {
+                                                                           MsmGeom g, uint32_t *buckets, int first, uint32_t slot_lo,
+                                                                           uint32_t slot_cnt) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
-    const uint32_t total = g.nwin * g.nbk;
-    for (uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += gridDim.x * blockDim.x) {
-        const uint32_t lo = offsets[gb], hi = offsets[gb + 1];
+    // slots [slot_lo, slot_lo + slot_cnt) = the (window, bucket) pairs of one window group; `offsets` is that group's table
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < slot_cnt; idx += gridDim.x * blockDim.x) {
+        const uint32_t gb = slot_lo + idx;
+        const uint32_t lo = offsets[idx], hi = offsets[idx + 1];
         Xyzz<F> acc = xyzz_infinity<F>();
         if (!first) {                                          // later chunk of a streamed MSM: continue the bucket
             if (lo == hi) continue;
@@ -389,34 +393,54 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     if (geom_n >= ((size_t)1 << 31) || n > geom_n) return ctx_fail(c, P2B_EARG, "msm: chunk must be < 2^31 terms");
     MsmGeom g = msm_geometry(geom_n ? geom_n : 1);
     const size_t cap_n = geom_n ? geom_n : 1;
+    if ((uint64_t)g.nwin * cap_n >= (1ull << 32)) return ctx_fail(c, P2B_EARG, "msm: too many terms for one pass (use the host entry point, which streams)");
     const size_t nslots = (size_t)g.nwin * g.nbk;
     const size_t xy = (size_t)4 * W * 4;                       // bytes per XYZZ point
     int rc;
     // msm_a: affine Montgomery points ; msm_b: hist | offsets | cursor ; msm_c: sorted entries ; msm_d: buckets | s1 | s2 | wsum
     if ((rc = dev_reserve(c, c->msm_a, cap_n * WU * 4))) return rc;
-    if ((rc = dev_reserve(c, c->msm_b, (3 * nslots + 4) * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_b, (3 * nslots + 16) * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * cap_n * 4))) return rc;
     const size_t nred = (size_t)g.nwin * g.tpw;
     if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin) * xy))) return rc;
     uint32_t *aff = (uint32_t *)c->msm_a.p;
-    uint32_t *hist = (uint32_t *)c->msm_b.p, *offsets = hist + nslots, *cursor = offsets + nslots + 1;
+    uint32_t *hist = (uint32_t *)c->msm_b.p, *cursor = hist + nslots, *offsets = cursor + nslots;   // offsets: nslots + one per group
     uint32_t *sorted = (uint32_t *)c->msm_c.p;
     uint32_t *buckets = (uint32_t *)c->msm_d.p, *s1 = buckets + nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
-    P2B_CUDA(c, cudaMemsetAsync(hist, 0, nslots * 4, c->stream));
     int grid = (int)((n + 255) / 256);
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
     if (grid < 1) grid = 1;
-    prof_begin(c, P2B_PROF_MSM_SORT);
-    k_msm_prepare<F><<<grid, 256, 0, c->stream>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
-    k_msm_hist<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base);
-    k_msm_scan<<<1, 1024, 0, c->stream>>>(hist, offsets, cursor, (uint32_t)nslots);
-    k_msm_scatter<<<grid, 256, 0, c->stream>>>((const uint32_t *)d_scalars, n, g, cursor, sorted);
-    prof_end(c, P2B_PROF_MSM_SORT, 4);
-    int agrid = (int)((nslots + 127) / 128);
-    prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
-    k_msm_accumulate<F><<<agrid, 128, 0, c->stream>>>(aff, offsets, sorted, g, buckets, (phase & MSM_FIRST) != 0);
-    prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
-    c->launches += 5;
+    // The windows are processed in groups: the counting sort of group i+1 (L2 atomics and scattered 4-byte stores, on the
+    // high-priority sort stream) overlaps the bucket accumulation of group i (multiplier bound, on the compute stream).
+    uint32_t ngroups = n >= ((size_t)1 << 18) ? 3 : 1;
+    if (ngroups > g.nwin) ngroups = g.nwin;
+    cudaStream_t S = ngroups > 1 ? c->sort_stream : c->stream, C = c->stream;
+    if (S != C) {
+        P2B_CUDA(c, cudaEventRecord(c->msm_ev[0], C));
+        P2B_CUDA(c, cudaStreamWaitEvent(S, c->msm_ev[0], 0));
+    }
+    prof_begin(c, P2B_PROF_MSM_SORT, S);
+    P2B_CUDA(c, cudaMemsetAsync(hist, 0, nslots * 4, S));
+    k_msm_prepare<F><<<grid, 256, 0, S>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
+    c->launches++;
+    for (uint32_t gi = 0; gi < ngroups; gi++) {
+        const uint32_t w_lo = g.nwin * gi / ngroups, w_hi = g.nwin * (gi + 1) / ngroups;
+        const uint32_t slot_lo = w_lo * g.nbk, slot_cnt = (w_hi - w_lo) * g.nbk;
+        uint32_t *offs = offsets + slot_lo + gi;
+        k_msm_hist<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base, w_lo, w_hi);
+        k_msm_scan<<<1, 1024, 0, S>>>(hist + slot_lo, offs, cursor + slot_lo, slot_cnt, (uint32_t)((size_t)w_lo * cap_n));
+        k_msm_scatter<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, cursor, sorted, w_lo, w_hi);
+        if (gi + 1 == ngroups) prof_end(c, P2B_PROF_MSM_SORT, (int)(1 + 3 * ngroups), S);
+        if (S != C) {
+            P2B_CUDA(c, cudaEventRecord(c->msm_ev[1 + gi], S));
+            P2B_CUDA(c, cudaStreamWaitEvent(C, c->msm_ev[1 + gi], 0));
+        }
+        const int agrid = (int)((slot_cnt + 127) / 128);
+        prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
+        k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt);
+        prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
+        c->launches += 4;
+    }
     if (!(phase & MSM_LAST)) {
         P2B_CUDA(c, cudaGetLastError());
         return P2B_OK;

@@ -22,6 +22,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_in = nullptr;      // H2D
     cudaStream_t copy_out = nullptr;     // D2H
+    cudaStream_t sort_stream = nullptr;  // MSM counting sort (high priority), overlapped with the bucket accumulation
+    cudaEvent_t msm_ev[4] = {};
     int sm_count = 148;
     std::string last_error;
     uint64_t err_index = 0;
@@ -54,8 +56,8 @@ int dev_reserve(Ctx *c, DevBuf &b, size_t bytes);
 int ctx_collect_error(Ctx *c);
 
 // brackets `kernels` launches queued between prof_begin / prof_end with timing events (no-ops unless profiling)
-void prof_begin(Ctx *c, int slot);
-void prof_end(Ctx *c, int slot, int kernels);
+void prof_begin(Ctx *c, int slot, cudaStream_t stream = nullptr);   // nullptr: c->stream
+void prof_end(Ctx *c, int slot, int kernels, cudaStream_t stream = nullptr);
 
 #define P2B_CUDA(c, call)                                     \
     do {                                                      \

@@ -12,7 +12,7 @@ cap() {  # name, kernel regex, skip, count, command...
 }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-extras --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-cap prof_msm_accumulate k_msm_accumulate 1 1 python bench.py --steps 1 --warmup 1 --no-extras --no-cpu
+cap prof_msm_accumulate k_msm_accumulate 3 3 python bench.py --steps 1 --warmup 1 --no-extras --no-cpu
 cap prof_batch_mul_g1 k_batch_mul 1 1 python tools/ncu_targets.py g1
 cap prof_batch_mul_g2 k_batch_mul 1 1 python tools/ncu_targets.py g2
 cap prof_fft k_fft_pass 0 3 python tools/ncu_targets.py fft
