@@ -195,6 +195,10 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: anything native libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     ctx = lib.Context(local_rank)
@@ -328,6 +332,8 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "one Pippenger MSM over 2^%d of the workload's terms (%.1f s), oracle/p2b_oracle.c "
                                               "= C restatement of bellman multiexp on all host threads" % (args.ref_log_n, dt)}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
