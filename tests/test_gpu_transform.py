@@ -168,3 +168,46 @@ def test_pot_decompress(ctx, oracle):
     bad[64 + 32 * 3] = 0x40                                             # infinity flag with stray bits
     with pytest.raises(DeserializationError):
         BatchedAccumulator.decompress(np.frombuffer(bytes(bad), dtype=np.uint8), out, False, params, ctx=ctx)
+
+
+def test_transform_composition_property_large(ctx):
+    """Size-independent check at 2^14 (82k G1 + 16k G2 points): contributing (tau1, alpha1, beta1) and then
+    (tau2, alpha2, beta2) gives exactly the response of one contribution with the products of the secrets."""
+    import hashlib
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    size = 14
+    params = CeremonyParams(size, 1024)
+    ch0 = np.zeros(params.accumulator_size, dtype=np.uint8)
+    o = 64
+    g1a, g2a = np.frombuffer(G1_GEN, dtype=np.uint8), np.frombuffer(G2_GEN, dtype=np.uint8)
+    for cnt, g in ((params.powers_g1_length, g1a), (params.powers_length, g2a), (params.powers_length, g1a),
+                   (params.powers_length, g1a), (1, g2a)):
+        ch0[o:o + cnt * g.size].reshape(cnt, g.size)[:] = g
+        o += cnt * g.size
+    k1, k2 = PrivateKey(TAU, ALPHA, BETA), PrivateKey(BETA + 5, TAU + 7, ALPHA + 11)
+    k12 = PrivateKey(k1.tau * k2.tau % R_MOD, k1.alpha * k2.alpha % R_MOD, k1.beta * k2.beta % R_MOD)
+    ch1 = np.zeros(params.accumulator_size, dtype=np.uint8)
+    BatchedAccumulator.transform(ch0, ch1, False, False, False, k1, params, ctx=ctx)
+    r2 = np.zeros(params.contribution_size, dtype=np.uint8)
+    BatchedAccumulator.transform(ch1, r2, False, True, True, k2, params, ctx=ctx)
+    r12 = np.zeros(params.contribution_size, dtype=np.uint8)
+    BatchedAccumulator.transform(ch0, r12, False, True, False, k12, params, ctx=ctx)
+    end = params.contribution_size - params.public_key_size
+    assert hashlib.blake2b(r2[64:end].tobytes()).digest() == hashlib.blake2b(r12[64:end].tobytes()).digest()
+    # and the endomorphism path for G2 agrees on the whole file
+    r12s = np.zeros(params.contribution_size, dtype=np.uint8)
+    BatchedAccumulator.transform(ch0, r12s, False, True, False, k12, params, ctx=ctx, g2_in_subgroup=True)
+    assert np.array_equal(r12s[64:end], r12[64:end])
+
+
+def test_transform_2_14_matches_oracle(ctx, oracle):
+    """Whole-file parity at 2^14 (the largest size the CPU oracle finishes in seconds)."""
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    size, batch = 14, 512
+    params = CeremonyParams(size, batch)
+    ch0 = oracle.pot_generate_initial(size)
+    exp = oracle.pot_transform(ch0, size, batch, be(TAU), be(ALPHA), be(BETA), threads=16)
+    out = np.zeros(params.contribution_size, dtype=np.uint8)
+    BatchedAccumulator.transform(np.frombuffer(ch0, dtype=np.uint8), out, False, True, False, PrivateKey(TAU, ALPHA, BETA),
+                                 params, ctx=ctx)
+    assert out[64:len(exp)].tobytes() == exp[64:]
