@@ -134,6 +134,37 @@ template <class F> __global__ void __launch_bounds__(128) k_recode(RecodeParams 
     }
 }
 
+// ------------------------------------------------------------------------------------------------- TMA tile staging
+// The point (and scalar) tile of a block is fetched by the TMA unit with ONE bulk asynchronous copy per array
+// (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) into a double buffer: while the block works
+// on tile t (milliseconds of arithmetic), tile t + gridDim.x is already in flight, so no thread ever waits on HBM and the
+// reads of the decompressed accumulator are full-line, perfectly coalesced bursts.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------- the hot kernel
 struct BatchMulParams {
     const uint32_t *in;
@@ -162,14 +193,14 @@ template <class F, int BLOCK> struct TablePolicy;
 #endif
 template <int BLOCK> struct TablePolicy<Fq, BLOCK> {
     static constexpr int MIN_BLOCKS = P2B_G1_MIN_BLOCKS;
-    static constexpr size_t SMEM = (size_t)BLOCK * 8 * 2 * 8 * 4;
+    static constexpr size_t TABLE_BYTES = (size_t)BLOCK * 8 * 2 * 8 * 4;
     static __device__ __forceinline__ StridedTable<Fq> make(uint32_t *smem, const BatchMulParams &) {
-        return StridedTable<Fq>{smem + threadIdx.x, BLOCK};   // private column: no barriers needed anywhere in this kernel
+        return StridedTable<Fq>{smem + threadIdx.x, BLOCK};   // private column per thread: the table needs no barriers
     }
 };
 template <int BLOCK> struct TablePolicy<Fq2, BLOCK> {
     static constexpr int MIN_BLOCKS = 2;
-    static constexpr size_t SMEM = 0;
+    static constexpr size_t TABLE_BYTES = 0;
     static __device__ __forceinline__ GlobalTable<Fq2> make(uint32_t *, const BatchMulParams &p) {
         return GlobalTable<Fq2>{p.gtable + (size_t)blockIdx.x * BLOCK + threadIdx.x, (size_t)gridDim.x * BLOCK};
     }
@@ -183,12 +214,52 @@ template <class F, int BLOCK, bool GLV> __global__ void __launch_bounds__(BLOCK,
     const int tid = threadIdx.x;
     const auto tbl = TablePolicy<F, BLOCK>::make(smem, p);
     const size_t ntiles = (p.n + BLOCK - 1) / BLOCK;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // staging area behind the table: 2 x point tile, 2 x scalar tile, 2 mbarriers
+    constexpr size_t TILE_WORDS = (size_t)BLOCK * WU, SC_WORDS = (size_t)BLOCK * 8;
+    uint32_t *stage = smem + TablePolicy<F, BLOCK>::TABLE_BYTES / 4;
+    uint32_t *pt_tile[2] = {stage, stage + TILE_WORDS};
+    uint32_t *sc_tile[2] = {stage + 2 * TILE_WORDS, stage + 2 * TILE_WORDS + SC_WORDS};
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 2 * TILE_WORDS + 2 * SC_WORDS);
+    auto issue = [&](size_t tile, int buf) {               // one elected thread: arm the barrier, start the bulk copies
+        const size_t first = tile * BLOCK, cnt = p.n - first < (size_t)BLOCK ? p.n - first : (size_t)BLOCK;
+        const uint32_t pb = (uint32_t)(cnt * WU * 4), sb = p.sc_mode == 0 ? (uint32_t)(cnt * 32) : 0u;
+        mbar_expect_tx(&bars[buf], pb + sb);
+        tma_load_1d(pt_tile[buf], p.in + first * WU, pb, &bars[buf]);
+        if (sb) tma_load_1d(sc_tile[buf], p.scalars + first * 8, sb, &bars[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && (size_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int buf = it & 1;
         const size_t i = tile * BLOCK + tid;
+        // every thread of the previous iteration has copied its operands out of buffer buf^1 (barrier at the end of the
+        // staging step below), so it can be refilled with the next tile while this one is being processed
+        if (tid == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, buf ^ 1);
+        mbar_wait(&bars[buf], (it >> 1) & 1);
+        uint32_t w[WU], sw[8];
+        if (i < p.n) {
+#pragma unroll
+            for (int j = 0; j < WU / 4; j++) {
+                uint4 v = reinterpret_cast<const uint4 *>(pt_tile[buf] + (size_t)tid * WU)[j];
+                w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+            }
+            if (p.sc_mode == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    uint4 v = reinterpret_cast<const uint4 *>(sc_tile[buf] + (size_t)tid * 8)[j];
+                    sw[4 * j] = v.x; sw[4 * j + 1] = v.y; sw[4 * j + 2] = v.z; sw[4 * j + 3] = v.w;
+                }
+            }
+        }
+        __syncthreads();
         if (i >= p.n) continue;
         // ---- point ----
-        uint32_t w[WU];
-        load_words<WU>(w, p.in + i * WU);
         Aff<F> a;
         bool inf;
         int rc = point_decode<F>(a, inf, w, p.in_enc, false);
@@ -200,8 +271,6 @@ template <class F, int BLOCK, bool GLV> __global__ void __launch_bounds__(BLOCK,
         // ---- scalar (canonical little-endian limbs) ----
         uint32_t k[8];
         if (p.sc_mode == 0) {
-            uint32_t sw[8];
-            load_words<8>(sw, p.scalars + i * 8);
             Fr kc = limbs_from_be_words<FrP>(sw);
             if (!is_canonical(kc)) report(p.err, p.err_base + i, P2B_EARG, 0);
 #pragma unroll
@@ -332,12 +401,14 @@ template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_i
         bp.tables = (const Fr *)c->tables.p;
         bp.start = sc.start;
     }
-    const size_t smem = TablePolicy<F, BLOCK>::SMEM;
+    // odd-multiples table (G1) + double-buffered point / scalar tiles + 2 mbarriers
+    const size_t smem = TablePolicy<F, BLOCK>::TABLE_BYTES + 2 * (size_t)BLOCK * (Wire<F>::WORDS_UNCOMPRESSED * 4 + 32) + 16;
     static bool attr_set = false;
     if (!attr_set && smem) {
         P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared));
+        if (TablePolicy<F, BLOCK>::TABLE_BYTES)
+            P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     size_t ntiles = (n + BLOCK - 1) / BLOCK;
