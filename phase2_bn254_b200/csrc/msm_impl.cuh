@@ -183,13 +183,37 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scal
     }
 }
 
+// Skewed inputs (many equal digits) would put most terms of a window into one bucket and serialise them on one thread.
+// A bucket thread therefore takes at most `seg` entries; the rest is cut into items of `chunk` entries that whole blocks
+// reduce (k_msm_heavy) and a last kernel folds into the bucket (k_msm_heavy_combine).  Uniform scalars never overflow
+// (seg = 8 x the average load), so the fast path only pays two empty launches.
+struct MsmHeavy {
+    uint32_t *counters;   // [0] items pushed, [1] heavy buckets pushed
+    uint4 *items;         // (bucket slot, first entry, end entry, -)
+    uint4 *hbuckets;      // (bucket slot, first item, item count, -)
+    uint32_t *partials;   // one XYZZ per item
+    uint32_t seg, chunk, cap_items, cap_buckets;
+};
+template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc, const uint32_t *aff, uint32_t ent) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
+    uint32_t w[WU];
+    ldw<WU>(w, aff + (size_t)(ent >> 1) * WU);
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < WU; j++) any |= w[j];
+    if (!any) return;                                          // point at infinity contributes nothing
+    Aff<F> q;
+#pragma unroll
+    for (int j = 0; j < W; j++) { set_word(q.x, j, w[j]); set_word(q.y, j, w[W + j]); }
+    q.y = cneg(q.y, (ent & 1u) != 0);
+    acc = xyzz_madd(acc, q);
+}
 #ifndef P2B_ACC_MIN_BLOCKS
 #define P2B_ACC_MIN_BLOCKS 1
 #endif
 template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
                                                                            MsmGeom g, uint32_t *buckets, int first, uint32_t slot_lo,
-                                                                           uint32_t slot_cnt) {
-    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
+                                                                           uint32_t slot_cnt, MsmHeavy hv, unsigned long long *err) {
     // slots [slot_lo, slot_lo + slot_cnt) = the (window, bucket) pairs of one window group; `offsets` is that group's table
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < slot_cnt; idx += gridDim.x * blockDim.x) {
         const uint32_t gb = slot_lo + idx;
@@ -199,22 +223,55 @@ template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_
             if (lo == hi) continue;
             acc = load_xyzz<F>(buckets, gb);
         }
+        const uint32_t mine = hi - lo > hv.seg ? lo + hv.seg : hi;
 #pragma unroll 1
-        for (uint32_t e = lo; e < hi; e++) {
-            const uint32_t ent = __ldg(sorted + e);
-            uint32_t w[WU];
-            ldw<WU>(w, aff + (size_t)(ent >> 1) * WU);
-            uint32_t any = 0;
-#pragma unroll
-            for (int j = 0; j < WU; j++) any |= w[j];
-            if (!any) continue;                                // point at infinity contributes nothing
-            Aff<F> q;
-#pragma unroll
-            for (int j = 0; j < W; j++) { set_word(q.x, j, w[j]); set_word(q.y, j, w[W + j]); }
-            q.y = cneg(q.y, (ent & 1u) != 0);
-            acc = xyzz_madd(acc, q);
-        }
+        for (uint32_t e = lo; e < mine; e++) accumulate_entry<F>(acc, aff, __ldg(sorted + e));
         store_xyzz<F>(buckets, gb, acc);
+        if (mine < hi) {                                       // overflow: hand the tail to k_msm_heavy
+            const uint32_t nit = (hi - mine + hv.chunk - 1) / hv.chunk;
+            const uint32_t fi = atomicAdd(&hv.counters[0], nit), hb = atomicAdd(&hv.counters[1], 1u);
+            if (fi + nit <= hv.cap_items && hb < hv.cap_buckets) {
+                for (uint32_t k = 0; k < nit; k++) {
+                    const uint32_t a = mine + k * hv.chunk, b = hi - a > hv.chunk ? a + hv.chunk : hi;
+                    hv.items[fi + k] = make_uint4(gb, a, b, 0u);
+                }
+                hv.hbuckets[hb] = make_uint4(gb, fi, nit, 0u);
+            } else report_err(err, gb, P2B_ECUDA, 0);          // cannot happen: the capacities cover the worst case
+        }
+    }
+}
+// one block per item: 128 partial sums, then a tree over shared memory
+template <class F> __global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *aff, const uint32_t *sorted, MsmHeavy hv) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    __shared__ __align__(16) uint32_t sm[128 * 4 * W];
+    const uint32_t count = hv.counters[0] < hv.cap_items ? hv.counters[0] : hv.cap_items;
+    for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
+        const uint4 item = hv.items[it];
+        Xyzz<F> acc = xyzz_infinity<F>();
+#pragma unroll 1
+        for (uint32_t e = item.y + threadIdx.x; e < item.z; e += 128) accumulate_entry<F>(acc, aff, __ldg(sorted + e));
+        store_xyzz<F>(sm, threadIdx.x, acc);
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t s = 64; s >= 1; s >>= 1) {
+            if (threadIdx.x < s) {
+                acc = xadd(acc, load_xyzz<F>(sm, threadIdx.x + s));
+                store_xyzz<F>(sm, threadIdx.x, acc);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_xyzz<F>(hv.partials, it, acc);
+        __syncthreads();
+    }
+}
+template <class F> __global__ void __launch_bounds__(128) k_msm_heavy_combine(uint32_t *buckets, MsmHeavy hv) {
+    const uint32_t count = hv.counters[1] < hv.cap_buckets ? hv.counters[1] : hv.cap_buckets;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint4 hb = hv.hbuckets[i];
+        Xyzz<F> acc = load_xyzz<F>(buckets, hb.x);
+#pragma unroll 1
+        for (uint32_t k = 0; k < hb.z; k++) acc = xadd(acc, load_xyzz<F>(hv.partials, hb.y + k));
+        store_xyzz<F>(buckets, hb.x, acc);
     }
 }
 
@@ -407,6 +464,26 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     uint32_t *hist = (uint32_t *)c->msm_b.p, *cursor = hist + nslots, *offsets = cursor + nslots;   // offsets: nslots + one per group
     uint32_t *sorted = (uint32_t *)c->msm_c.p;
     uint32_t *buckets = (uint32_t *)c->msm_d.p, *s1 = buckets + nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
+    // overflow handling for skewed digit distributions (see MsmHeavy)
+    MsmHeavy hv;
+    {
+        const size_t load = cap_n / g.nb + 1;                 // average terms per bucket of a wide window
+        hv.seg = (uint32_t)(8 * load < 256 ? 256 : 8 * load);
+        hv.chunk = 1u << 15;
+        if (const char *e = getenv("P2B_MSM_SEG")) {           // test hook: tiny segments exercise the overflow path
+            int v = atoi(e);
+            if (v > 0) { hv.seg = (uint32_t)v; hv.chunk = (uint32_t)(4 * v); }
+        }
+        const size_t total = (size_t)g.nwin * cap_n;
+        hv.cap_items = (uint32_t)(total / hv.chunk + total / hv.seg + 16);
+        hv.cap_buckets = (uint32_t)(total / hv.seg + 16);
+        if ((rc = dev_reserve(c, c->msm_e, 64 + ((size_t)hv.cap_items + hv.cap_buckets) * 16 + (size_t)hv.cap_items * xy))) return rc;
+        char *hp = (char *)c->msm_e.p;
+        hv.counters = (uint32_t *)hp;
+        hv.items = (uint4 *)(hp + 64);
+        hv.hbuckets = hv.items + hv.cap_items;
+        hv.partials = (uint32_t *)(hv.hbuckets + hv.cap_buckets);
+    }
     int grid = (int)((n + 255) / 256);
     if (grid > c->sm_count * 16) grid = c->sm_count * 16;
     if (grid < 1) grid = 1;
@@ -437,9 +514,12 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         }
         const int agrid = (int)((slot_cnt + 127) / 128);
         prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
-        k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt);
-        prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
-        c->launches += 4;
+        P2B_CUDA(c, cudaMemsetAsync(hv.counters, 0, 8, C));
+        k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt, hv, c->d_err);
+        k_msm_heavy<F><<<c->sm_count * 4, 128, 0, C>>>(aff, sorted, hv);
+        k_msm_heavy_combine<F><<<8, 128, 0, C>>>(buckets, hv);
+        prof_end(c, P2B_PROF_MSM_ACCUMULATE, 3);
+        c->launches += 6;
     }
     if (!(phase & MSM_LAST)) {
         P2B_CUDA(c, cudaGetLastError());

@@ -32,7 +32,7 @@ struct Ctx {
     unsigned long long *d_err = nullptr;   // device error word
     unsigned long long *h_err = nullptr;   // pinned mirror
     // growable device scratch
-    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, fft_tw, gtable, gfft;
+    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, fft_tw, gtable, gfft;
     // pinned host staging for pageable caller buffers
     void *h_pin[2] = {nullptr, nullptr};
     size_t h_pin_cap[2] = {0, 0};

@@ -111,3 +111,22 @@ def test_power_pairs(ctx, oracle, group):
     assert a == oracle.msm(group, v[: (n - 1) * size], sc, threads=8)
     assert b == oracle.msm(group, v[size:], sc, threads=8)
     assert b == oracle.point_mul(group, a, tau)
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_msm_skewed_scalars(ctx, oracle, group, monkeypatch):
+    """Equal scalars put every term of a window into ONE bucket: the per-thread segment cap hands the tail to the
+    block-level heavy-bucket path.  Also forced with tiny segments on random scalars (several items per bucket)."""
+    n = 6000 if group == 0 else 2500
+    pts = random_points(oracle, group, n, seed=95)
+    k = be(0x1234567890abcdef1234567890abcdef1234567890abcdef1234567 % R_MOD)
+    assert ctx.msm(group, pts, k * n) == oracle.msm(group, pts, k * n, threads=8)
+    mixed = k * (n // 2) + random_scalars(n - n // 2, seed=96)
+    assert ctx.msm(group, pts, mixed) == oracle.msm(group, pts, mixed, threads=8)
+    monkeypatch.setenv("P2B_MSM_SEG", "3")
+    sc = random_scalars(n, seed=97)
+    exp = oracle.msm(group, pts, sc, threads=8)
+    assert ctx.msm(group, pts, sc) == exp
+    monkeypatch.setenv("P2B_MSM_STREAM_CHUNK", "1000")          # streamed chunks continue the same buckets
+    assert ctx.msm(group, pts, sc) == exp
+    assert ctx.msm(group, pts, k * n) == oracle.msm(group, pts, k * n, threads=8)

@@ -54,6 +54,8 @@ def msm_probe(lg, group=0):
     g = torch.Generator(device="cuda"); g.manual_seed(lg)
     sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
     sc[:, 0] &= 0x1f
+    if os.environ.get("SKEW"):          # every scalar equal: one bucket per window receives all n terms
+        sc[:] = sc[0].clone()
     torch.cuda.synchronize()
     ts = []
     for it in range(4):
