@@ -407,8 +407,13 @@ static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_
     if ((rc = phase2_transcript(c, params, len, delta, s, pk_s_delta, pk_transcript))) return rc;
     if ((rc = single_mul(c, 1, r_g2, delta, pk_r_delta))) return rc;
     if ((rc = single_mul(c, 0, params + L.delta_g1, delta, pk_delta_after))) return rc;
-    // everything that does not change is copied through
-    if (out != params) memcpy(out, params, len);
+    // everything that does not change is copied through (h and l are rewritten below: skip their 64 * (h_n + l_n) bytes)
+    if (out != params) {
+        const uint64_t h_end = L.h_off + L.h_n * 64, l_end = L.l_off + L.l_n * 64;
+        memcpy(out, params, L.h_off);
+        memcpy(out + h_end, params + h_end, L.l_off - h_end);
+        memcpy(out + l_end, params + l_end, len - l_end);
+    }
     // l and h scaled by delta^-1 (parameters.rs:499-505); infinity tolerated (no assert in the phase-2 batch_exp)
     const struct { uint64_t off, n; } vecs[2] = {{L.l_off, L.l_n}, {L.h_off, L.h_n}};
     for (int v = 0; v < 2; v++) {
