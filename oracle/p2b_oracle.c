@@ -4,8 +4,8 @@
  * `--impl reference` legs may load this library, and only as the checker or the timed CPU
  * baseline.  The product library (phase2_bn254_b200/csrc -> libp2b.so) never links it.
  *
- * PARITY PIN: the reference holds no stored output bytes for this path; this
- * oracle is pinned by (1) the Montgomery / generator / curve constants hard-coded in
+ * PARITY PIN -- "parity unpinned" by reference-produced output bytes: the reference holds no stored output
+ * bytes for this path and cannot be run here.  This oracle is pinned by (1) the Montgomery / generator / curve constants hard-coded in
  * pairing/src/bn256/fq.rs, fq2.rs, ec.rs, fr.rs; (2) an independent big-int implementation
  * (oracle/bn254_ref.py) on randomised cases; (3) the reference tests' relations (curve.rs
  * add/double/mul/wnaf/encoding round trips, domain.rs fft∘ifft = id, multiexp == naive sum).
@@ -22,7 +22,9 @@
  *   batch_exp (phase 2)                phase2/src/parameters.rs:424-470
  *   multiexp (Pippenger)               bellman/src/multiexp.rs:53-157, 330-355
  *   serial_fft / parallel_fft / ifft   bellman/src/domain.rs:154-195, 263-376
- * Threading follows the reference: static chunks of len/ncpus on threads.
+ * Threading follows the reference: static chunks of len/ncpus on threads (batch_exp, FFT); the
+ * Pippenger tasks (window x point-chunk) are handed out dynamically like bellman's CpuPool futures.
+ * (4) golden vectors tests/golden/vectors.json generated from the big-int implementation.
  */
 #include <math.h>
 #include <pthread.h>
