@@ -404,17 +404,10 @@ static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_
     uint8_t *pk_delta_after = pubkey, *pk_s = pubkey + 64, *pk_s_delta = pubkey + 128, *pk_r_delta = pubkey + 192,
             *pk_transcript = pubkey + 320;
     memcpy(pk_s, s, 64);
-    if ((rc = phase2_transcript(c, params, len, delta, s, pk_s_delta, pk_transcript))) return rc;
-    if ((rc = single_mul(c, 1, r_g2, delta, pk_r_delta))) return rc;
-    if ((rc = single_mul(c, 0, params + L.delta_g1, delta, pk_delta_after))) return rc;
-    // everything that does not change is copied through (h and l are rewritten below: skip their 64 * (h_n + l_n) bytes)
-    if (out != params) {
-        const uint64_t h_end = L.h_off + L.h_n * 64, l_end = L.l_off + L.l_n * 64;
-        memcpy(out, params, L.h_off);
-        memcpy(out + h_end, params + h_end, L.l_off - h_end);
-        memcpy(out + l_end, params + l_end, len - l_end);
-    }
-    // l and h scaled by delta^-1 (parameters.rs:499-505); infinity tolerated (no assert in the phase-2 batch_exp)
+    if ((rc = begin_call(c))) return rc;
+    // l and h scaled by delta^-1 (parameters.rs:499-505); infinity tolerated (no assert in the phase-2 batch_exp).  All GPU
+    // work of the call is queued first and collected once: the two big jobs, then the four single multiplications by delta
+    // (s, delta_g1 in G1; r, delta_g2 in G2) as two 2-point jobs.
     const struct { uint64_t off, n; } vecs[2] = {{L.l_off, L.l_n}, {L.h_off, L.h_n}};
     for (int v = 0; v < 2; v++) {
         HostJob j;
@@ -425,12 +418,41 @@ static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_
         memcpy(j.sc.k, dinv.l, 32);
         if ((rc = run_host_job(c, j))) return rc;
     }
+    uint8_t g1_in[128], g1_out[128], g2_in[256], g2_out[256];
+    memcpy(g1_in, s, 64); memcpy(g1_in + 64, params + L.delta_g1, 64);
+    memcpy(g2_in, r_g2, 128); memcpy(g2_in + 128, params + L.delta_g2, 128);
+    for (int g2 = 0; g2 < 2; g2++) {
+        HostJob j;
+        memset(&j, 0, sizeof j);
+        j.g2 = g2; j.in = g2 ? g2_in : g1_in; j.out = g2 ? g2_out : g1_out; j.n = 2;
+        j.in_enc = P2B_ENC_UNCOMPRESSED; j.out_enc = P2B_ENC_UNCOMPRESSED; j.flags = P2B_CHECK_INPUT;
+        j.sc.mode = 1;
+        memcpy(j.sc.k, dk, 32);
+        if ((rc = run_host_job(c, j))) return rc;
+    }
+    // everything that does not change is copied through while the GPU works (h and l are rewritten by the jobs above)
+    if (out != params) {
+        const uint64_t h_end = L.h_off + L.h_n * 64, l_end = L.l_off + L.l_n * 64;
+        memcpy(out, params, L.h_off);
+        memcpy(out + h_end, params + h_end, L.l_off - h_end);
+        memcpy(out + l_end, params + l_end, len - l_end);
+    }
     if ((rc = ctx_collect_error(c))) return rc;
+    // keypair (parameters.rs:860-908): s_delta, the transcript hash H(cs_hash | contributions | s | s_delta), r_delta, delta_after
+    memcpy(pk_s_delta, g1_out, 64);
+    memcpy(pk_delta_after, g1_out + 64, 64);
+    memcpy(pk_r_delta, g2_out, 128);
+    {
+        Blake2b h;
+        h.update(params + L.cs_hash, 64);
+        h.update(params + L.contrib_off, L.contrib_n * 384);
+        h.update(s, 64);
+        h.update(pk_s_delta, 64);
+        h.finish(pk_transcript);
+    }
     // vk.delta_g1 / vk.delta_g2 *= delta (parameters.rs:507-508)
     memcpy(out + L.delta_g1, pk_delta_after, 64);
-    uint8_t dg2[128];
-    if ((rc = single_mul(c, 1, params + L.delta_g2, delta, dg2))) return rc;
-    memcpy(out + L.delta_g2, dg2, 128);
+    memcpy(out + L.delta_g2, g2_out + 128, 128);
     // contributions.push(pubkey)
     wr_u32be(out + L.contrib_count_off, (uint32_t)(L.contrib_n + 1));
     memcpy(out + len, pubkey, 384);

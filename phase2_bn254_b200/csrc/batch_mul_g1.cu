@@ -29,12 +29,16 @@ int launch_batch_mul_g2(Ctx *c, const void *d_in, void *d_out, size_t n, const S
 int launch_batch_mul_g2_glv(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc, int out_enc,
                             int flags, uint64_t err_index_base);
 
+int launch_batch_mul_g1_uniform(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc, int out_enc,
+                                int flags, uint64_t err_index_base);
+
 int launch_batch_mul(Ctx *c, int g2, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc,
                      int out_enc, int flags, uint64_t err_index_base) {
     if (n == 0) return P2B_OK;
     if (in_enc < 0 || in_enc > 2 || out_enc < 0 || out_enc > 2) return ctx_fail(c, P2B_EARG, "bad encoding");
     if (g2 && (flags & P2B_G2_SUBGROUP)) return launch_batch_mul_g2_glv(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
     if (g2) return launch_batch_mul_g2(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
+    if (sc.mode == 1 && n >= 1024) return launch_batch_mul_g1_uniform(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
     return launch_typed<Fq, G1_BLOCK, true>(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base);
 }
 

@@ -180,6 +180,7 @@ struct BatchMulParams {
     unsigned long long *err;
     uint64_t err_base;
     uint4 *gtable;             // G2: per-thread odd-multiples tables in global memory (grid * block columns)
+    UniformDigits uni;         // UNIFORM kernels (mode 1): width-5 NAF of the GLV halves of the one scalar
 };
 
 // table policy: G1 keeps its 512 B / thread table in shared memory; G2 (1 KB / thread) keeps it in L2 so that two
@@ -207,7 +208,8 @@ template <int BLOCK> struct TablePolicy<Fq2, BLOCK> {
 };
 
 // GLV: use the endomorphism split (always for G1; for G2 only when the caller vouches for subgroup membership)
-template <class F, int BLOCK, bool GLV> __global__ void __launch_bounds__(BLOCK, TablePolicy<F, BLOCK>::MIN_BLOCKS) k_batch_mul(BatchMulParams p) {
+// UNIFORM: every point is multiplied by the same scalar (mode 1) -> warp-uniform sparse digits (mul_glv_uniform)
+template <class F, int BLOCK, bool GLV, bool UNIFORM = false> __global__ void __launch_bounds__(BLOCK, TablePolicy<F, BLOCK>::MIN_BLOCKS) k_batch_mul(const __grid_constant__ BatchMulParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     constexpr bool IS_G1 = FieldTraits<F>::WORDS == 8;
@@ -296,7 +298,8 @@ template <class F, int BLOCK, bool GLV> __global__ void __launch_bounds__(BLOCK,
             F zr[8];
             bool bad = !oncurve;      // off-curve garbage (unchecked mode): GLV does not apply
             if (!bad) {
-                if constexpr (GLV) r = mul_glv<F>(a, k, tbl, zr, bad);
+                if constexpr (UNIFORM) r = mul_glv_uniform<F>(a, p.uni, tbl, zr, bad);
+                else if constexpr (GLV) r = mul_glv<F>(a, k, tbl, zr, bad);
                 else r = mul_window4<F>(a, k, tbl, zr, bad);
             }
             if (bad) mul_binary_slow<F>(&r, &a, k);
@@ -354,7 +357,7 @@ template <class F> __global__ void __launch_bounds__(128) k_normalize(NormalizeP
 static constexpr int G1_BLOCK = P2B_G1_BLOCK;
 static constexpr int G2_BLOCK = 128;
 
-template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc,
+template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc,
                                                        int in_enc, int out_enc, int flags, uint64_t err_base) {
     constexpr int W = FieldTraits<F>::WORDS;
     constexpr bool IS_G2 = W == 16;
@@ -389,7 +392,10 @@ template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_i
     bp.in = in_words; bp.jx = jx; bp.jy = jy; bp.jz = jz; bp.n = n; bp.in_enc = kin_enc; bp.flags = flags;
     bp.sc_mode = sc.mode; bp.err = c->d_err; bp.err_base = err_base;
     if (sc.mode == 0) bp.scalars = (const uint32_t *)sc.d_scalars;
-    else if (sc.mode == 1) memcpy(bp.k, sc.k, 32);
+    else if (sc.mode == 1) {
+        memcpy(bp.k, sc.k, 32);
+        if (UNIFORM) bp.uni = uniform_digits(sc.k);
+    }
     else {
         if ((rc = dev_reserve(c, c->tables, 4096 * sizeof(Fr) + 64))) return rc;
         uint32_t *d_tc = (uint32_t *)((char *)c->tables.p + 4096 * sizeof(Fr));
@@ -405,9 +411,9 @@ template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_i
     const size_t smem = TablePolicy<F, BLOCK>::TABLE_BYTES + 2 * (size_t)BLOCK * (Wire<F>::WORDS_UNCOMPRESSED * 4 + 32) + 16;
     static bool attr_set = false;
     if (!attr_set && smem) {
-        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (TablePolicy<F, BLOCK>::TABLE_BYTES)
-            P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV, UNIFORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
@@ -420,7 +426,7 @@ template <class F, int BLOCK, bool GLV> int launch_typed(Ctx *c, const void *d_i
     }
     if (grid > 0) {
         prof_begin(c, P2B_PROF_BATCH_MUL);
-        k_batch_mul<F, BLOCK, GLV><<<grid, BLOCK, smem, c->stream>>>(bp);
+        k_batch_mul<F, BLOCK, GLV, UNIFORM><<<grid, BLOCK, smem, c->stream>>>(bp);
         prof_end(c, P2B_PROF_BATCH_MUL, 1);
         c->launches++;
         // ~32 points per thread in the normalisation pass, at least one full wave of 128-thread blocks

@@ -314,6 +314,71 @@ template <class F, class Tbl> P2B_HD Jac<F> mul_glv(const Aff<F> &p, const uint3
     return acc;
 }
 
+// ------------------------------------------------------------------ one scalar for every point (phase-2 shape)
+// When all lanes multiply by the SAME scalar (MPCParameters::contribute: every H and L point times delta^-1,
+// phase2/src/parameters.rs:424-470) the digit pattern is warp-uniform, so zero digits can simply be skipped without
+// divergence: the host recodes the two GLV halves into width-5 NAF (odd digits in [-15, 15], on average one non-zero
+// digit in six) and the kernel runs 128 doublings + ~43 mixed adds instead of 128 + 66.  Digits are LSB first.
+struct UniformDigits {
+    int8_t d1[136], d2[136];
+    int len;
+};
+template <int N> P2B_HD int wnaf5_recode(int8_t *out, uint32_t *m) {      // m: N-word magnitude, destroyed
+    int len = 0;
+    for (int i = 0; i < 32 * N + 1; i++) {
+        int8_t d = 0;
+        if (m[0] & 1u) {
+            int v = (int)(m[0] & 31u);
+            if (v >= 16) v -= 32;
+            d = (int8_t)v;
+            if (v > 0) {                                               // m -= v
+                uint64_t br = (uint64_t)v;
+                for (int j = 0; j < N && br; j++) { uint64_t t = (uint64_t)m[j] - br; m[j] = (uint32_t)t; br = (t >> 63) & 1; }
+            } else {                                                   // m += -v
+                uint64_t c = (uint64_t)(-v);
+                for (int j = 0; j < N && c; j++) { c += m[j]; m[j] = (uint32_t)c; c >>= 32; }
+            }
+        }
+        out[i] = d;
+        if (d) len = i + 1;
+        for (int j = 0; j < N; j++) m[j] = (m[j] >> 1) | (j + 1 < N ? m[j + 1] << 31 : 0u);
+    }
+    return len;
+}
+P2B_HD UniformDigits uniform_digits(const uint32_t k[8]) {
+    GlvSplit s = glv_decompose(k);
+    UniformDigits u;
+    uint32_t m1[6] = {s.k1[0], s.k1[1], s.k1[2], s.k1[3], s.k1[4], 0}, m2[6] = {s.k2[0], s.k2[1], s.k2[2], s.k2[3], s.k2[4], 0};
+    for (int i = 0; i < 136; i++) { u.d1[i] = 0; u.d2[i] = 0; }
+    int l1 = wnaf5_recode<5>(u.d1, m1), l2 = wnaf5_recode<5>(u.d2, m2);
+    if (s.neg1) for (int i = 0; i < l1; i++) u.d1[i] = (int8_t)-u.d1[i];
+    if (s.neg2) for (int i = 0; i < l2; i++) u.d2[i] = (int8_t)-u.d2[i];
+    u.len = l1 > l2 ? l1 : l2;
+    return u;
+}
+template <class F, class Tbl> P2B_HD Jac<F> mul_glv_uniform(const Aff<F> &p, const UniformDigits &u, const Tbl &tbl, F *zr, bool &bad) {
+    F zg = build_odd_table<F>(p, tbl, zr, bad);
+    Jac<F> acc = jac_infinity<F>();
+#pragma unroll 1
+    for (int i = u.len - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        const int a = u.d1[i], b = u.d2[i];                            // warp-uniform
+        if (a) {
+            Aff<F> q = tbl.get(((a < 0 ? -a : a) - 1) >> 1);
+            q.y = cneg(q.y, a < 0);
+            acc = jac_madd(acc, q);
+        }
+        if (b) {
+            Aff<F> q = tbl.get(((b < 0 ? -b : b) - 1) >> 1);
+            q.x = endo_x(q.x);
+            q.y = cneg(q.y, b < 0);
+            acc = jac_madd(acc, q);
+        }
+    }
+    acc.z = mul(acc.z, zg);
+    return acc;
+}
+
 template <class Tbl> P2B_HD Jac<Fq> g1_mul_glv(const Aff<Fq> &p, const uint32_t k[8], const Tbl &tbl, Fq *zr, bool &bad) {
     return mul_glv<Fq>(p, k, tbl, zr, bad);
 }

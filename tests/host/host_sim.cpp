@@ -39,6 +39,7 @@ int sim_point_mul(int g2, const uint8_t *in, const uint8_t *k_be, uint8_t *out, 
         if (inf) r = jac_infinity<Fq>();
         else if (path == 0) r = g1_mul_glv(p, k, tbl, zr, bad);
         else if (path == 1) r = mul_window4<Fq>(p, k, tbl, zr, bad);
+        else if (path == 4) { UniformDigits u = uniform_digits(k); r = mul_glv_uniform<Fq>(p, u, tbl, zr, bad); }
         else r = mul_binary<Fq>(p, k);
         Aff<Fq> a; bool oinf; to_affine(r, a, oinf);
         uint32_t ow[16]; point_encode<Fq>(ow, a, oinf, out_enc);

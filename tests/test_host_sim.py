@@ -62,7 +62,8 @@ def test_scalar_mul_paths_vs_oracle(sim, oracle, group):
     exp_c = oracle.batch_mul(group, pts, b"".join(be(k) for k in ks), 0, 1, threads=8)
     for i, k in enumerate(ks):
         p = pts[i * size:(i + 1) * size]
-        for path in (0, 1, 2) + ((3,) if group else ()):      # 3 = opt-in endomorphism split on G2 (subgroup points)
+        # 3 = opt-in endomorphism split on G2 (subgroup points); 4 = uniform-scalar width-5 NAF path (G1, phase-2 shape)
+        for path in (0, 1, 2) + ((3,) if group else (4,)):
             got, bad = _mul(sim, group, p, be(k), path)
             if not bad:      # `bad` routes to the complete binary path in the kernel
                 assert got == exp[i * size:(i + 1) * size], (group, path, hex(k))
