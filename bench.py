@@ -286,9 +286,11 @@ def run_ours(args, rank, world, local_rank):
     acc_ms, acc_k = prof["accumulate"]
     acc_avg_ms = acc_ms / max(1, args.steps)       # the accumulation of one MSM (one launch per window group)
     achieved = 96.0 * n / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms else None
-    traffic = None
+    traffic = pipe_busy = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_msm_accumulate<Fq>@2^%d" % args.log_n)
+        prof_json = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = prof_json.get("k_msm_accumulate<Fq>@2^%d" % args.log_n)
+        pipe_busy = prof_json.get("k_msm_accumulate<Fq>@2^%d:fmaheavy_busy" % args.log_n)
     except (OSError, ValueError):
         pass
     line = {
@@ -306,8 +308,11 @@ def run_ours(args, rank, world, local_rank):
                      "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 5) if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 96 * n,
                      "kernel_ms": round(acc_avg_ms, 4), "launches_per_step": int(acc_k // max(1, args.steps)),
-                     "note": "integer-ALU bound (IMAD), not HBM bound: see DESIGN.md; share of step = %.2f" %
-                             (acc_avg_ms / dev_ms if dev_ms else 0)},
+                     "limiting_pipe": {"pipe": "fma-heavy (IMAD.WIDE)", "busy_frac": pipe_busy,
+                                       "source": "ncu capture committed under profiles/ (not measured live)"},
+                     "note": "bound by the integer multiplier pipe, not by HBM (see DESIGN.md section 4); traffic = DRAM bytes "
+                             "of the accumulation of one MSM from the ncu capture; kernel time / step time = %.2f (the "
+                             "sort of the next window group runs concurrently)" % (acc_avg_ms / dev_ms if dev_ms else 0)},
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
         "result_x": result["r"][:32].hex(),
     }

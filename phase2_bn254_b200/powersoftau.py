@@ -16,6 +16,9 @@ import numpy as np
 from . import lib as _lib
 
 
+_FQ = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+
+
 class UseCompression:
     Yes, No = True, False
 
@@ -80,6 +83,34 @@ class BatchedAccumulator:
         if cls._ctx is None or cls._ctx.device != device:
             cls._ctx = _lib.Context(device)
         return cls._ctx
+
+    @staticmethod
+    def generate_initial(output_map, compress_the_output, parameters):
+        """The initial accumulator of new_constrained: every element is the group generator
+        (batched_accumulator.rs:1295-1347).  Writes output_map[64:]; the blank-hash prefix is the caller's
+        (new_constrained.rs:56-63).  Pure byte replication -- no arithmetic, runs on the host."""
+        g1 = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")                      # G1 generator (1, 2), ec.rs:1013-1051
+        g2 = b"".join(v.to_bytes(32, "big") for v in (                              # G2 generator, fq.rs:54-83 (c1 first)
+            11559732032986387107991004021392285783925812861821192530917403151452391805634,
+            10857046999023057135944570762232829481370756359578518086990519993285655852781,
+            4082367875863433681332203403145435568316851327593401208105741076214120093531,
+            8495653923123431417604973247489272438418190587263600148770280649306958101930))
+        if compress_the_output:
+            g1c = bytearray(g1[:32])
+            if 2 > _FQ - 2:
+                g1c[0] |= 0x80
+            y1, y0 = int.from_bytes(g2[64:96], "big"), int.from_bytes(g2[96:128], "big")
+            larger = (y1 > _FQ - y1) if y1 else (y0 > _FQ - y0)                      # Fq2 order: c1 then c0 (fq2.rs:21-30)
+            g2c = bytearray(g2[:64])
+            if larger:
+                g2c[0] |= 0x80
+            g1, g2 = bytes(g1c), bytes(g2c)
+        a1, a2 = np.frombuffer(g1, dtype=np.uint8), np.frombuffer(g2, dtype=np.uint8)
+        p = parameters
+        o = 64
+        for cnt, g in ((p.powers_g1_length, a1), (p.powers_length, a2), (p.powers_length, a1), (p.powers_length, a1), (1, a2)):
+            output_map[o:o + cnt * g.size].reshape(cnt, g.size)[:] = g
+            o += cnt * g.size
 
     @classmethod
     def decompress(cls, input_map, output_map, check_input_for_correctness, parameters, ctx=None, shard_index=0,

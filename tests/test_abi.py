@@ -66,3 +66,32 @@ def test_geometry_matches_reference_table():
         assert p.accumulator_size == acc and p.contribution_size == contrib
         assert so.p2b_pot_accumulator_size(size, 0) == acc
         assert so.p2b_pot_accumulator_size(size, 1) == contrib - 768
+
+
+def test_generate_initial_matches_oracle(oracle):
+    """Host-only mirror of BatchedAccumulator::generate_initial (batched_accumulator.rs:1295-1347), both encodings."""
+    import hashlib
+    import numpy as np
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams
+    for size in (1, 4, 7):
+        p = CeremonyParams(size, 16)
+        for compressed in (False, True):
+            n = p.contribution_size - p.public_key_size if compressed else p.accumulator_size
+            out = np.zeros(n, dtype=np.uint8)
+            out[:64] = np.frombuffer(hashlib.blake2b(b"").digest(), dtype=np.uint8)
+            BatchedAccumulator.generate_initial(out, compressed, p)
+            assert out.tobytes() == oracle.pot_generate_initial(size, compressed)
+
+
+def test_params_layout_host_logic():
+    import struct
+    from phase2_bn254_b200.phase2 import params_layout
+    body = bytes(64 + 64 + 128 + 128 + 64 + 128)
+    vecs = b"".join(struct.pack(">I", n) + bytes(n * sz) for n, sz in ((2, 64), (3, 64), (4, 64), (1, 64), (1, 64), (1, 128)))
+    buf = body + vecs + bytes(64) + struct.pack(">I", 1) + bytes(384)
+    lay = params_layout(buf)
+    assert lay["h"][1] == 3 and lay["l"][1] == 4 and lay["contributions"][1] == 1 and lay["b_g2"][2:] == (128, 1)
+    with pytest.raises(ValueError):
+        params_layout(buf + b"x")
+    with pytest.raises(ValueError):
+        params_layout(buf[:-1])

@@ -211,3 +211,28 @@ def test_transform_2_14_matches_oracle(ctx, oracle):
     BatchedAccumulator.transform(np.frombuffer(ch0, dtype=np.uint8), out, False, True, False, PrivateKey(TAU, ALPHA, BETA),
                                  params, ctx=ctx)
     assert out[64:len(exp)].tobytes() == exp[64:]
+
+
+def test_mpc_parameters_read_checked(ctx):
+    """MPCParameters::read: checked deserialisation of every section on the GPU (groth16/mod.rs:287-383)."""
+    import json
+    import os
+    from phase2_bn254_b200.phase2 import MPCParameters, params_layout
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))["phase2"]
+    good = bytes.fromhex(gold["c1"]["out"])
+    mp = MPCParameters.read(good, False, True, ctx=ctx)                       # h[2] is infinity: allowed by default
+    assert mp.data.tobytes() == good
+    with pytest.raises(IOError) as e:
+        MPCParameters.read(good, True, True, ctx=ctx)
+    assert "point at infinity in h[2]" in str(e.value)
+    lay = params_layout(good)
+    bad = bytearray(good)
+    bad[lay["b_g2"][0] + 128 + 127] ^= 1                                       # b_g2[1] off the curve
+    with pytest.raises(IOError) as e:
+        MPCParameters.read(bytes(bad), False, True, ctx=ctx)
+    assert "NotOnCurve in b_g2[1]" in str(e.value)
+    MPCParameters.read(bytes(bad), False, False, ctx=ctx)                      # unchecked accepts it (into_affine_unchecked)
+    bad = bytearray(good)
+    bad[lay["a"][0]: lay["a"][0] + 32] = (2**256 - 1).to_bytes(32, "big")      # flag bits + coordinate >= q
+    with pytest.raises(IOError):
+        MPCParameters.read(bytes(bad), False, False, ctx=ctx)
