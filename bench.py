@@ -193,6 +193,7 @@ def run_ours(args, rank, world, local_rank):
     from phase2_bn254_b200 import dist as pdist
     from phase2_bn254_b200 import lib
 
+    numa_cores = pdist.bind_to_gpu_numa(local_rank) if world > 1 else None    # pinned buffers land next to the GPU
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     # stdout carries exactly one JSON line: anything native libraries print there (e.g. NCCL's version banner) goes to stderr
@@ -301,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
                    "scalars": "uniform mod r (32 B BE)", "arithmetic": "8 x u32 limbs, 256-bit Montgomery, integer only", "l2": "inputs (%.1f GB) exceed L2" % (96.0 * n / 1e9),
                    "parallelism": "point-range shards + all-gather of per-rank results" if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 96 * n, "d2h_bytes_per_step": 64,
-                "ms_per_step": round(e2e_ms, 4)},
+                "ms_per_step": round(e2e_ms, 4), "host_numa_binding": bool(numa_cores)},
         "gpu_launches": int(launches),
         "clocks": clocks.window(t_w0, t_w1),
         "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fq>", "achieved": round(achieved, 2) if achieved else None,

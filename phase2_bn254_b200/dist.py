@@ -23,6 +23,37 @@ def shard_range(count, index, shards):
     return lo, lo + per + (1 if index < rem else 0)
 
 
+def bind_to_gpu_numa(local_rank):
+    """Restrict this process to the CPU cores next to its GPU (the "CPU Affinity" column of `nvidia-smi topo -m`) so that
+    the pinned host buffers it allocates afterwards are first-touched on that NUMA node and H2D copies do not cross the
+    socket interconnect.  Returns the core list, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    if "CPU Affinity" not in out:
+        return None
+    for line in out.splitlines():
+        fields = line.split()
+        if not fields or fields[0] != "GPU%d" % local_rank:
+            continue
+        for f in fields[1:]:                    # link types (X, NV18, SYS, ...) never start with a digit; the core list does
+            if f[0].isdigit() and all(ch.isdigit() or ch in "-," for ch in f):
+                cores = set()
+                for part in f.split(","):
+                    a, _, b = part.partition("-")
+                    cores.update(range(int(a), int(b or a) + 1))
+                allowed = cores & os.sched_getaffinity(0)
+                if allowed:
+                    os.sched_setaffinity(0, allowed)
+                    return sorted(allowed)
+                return None
+        return None
+    return None
+
+
 def all_gather_bytes(payload, group=None, device=None):
     """All-gather of one fixed-size byte string per rank over torch.distributed (NCCL on GPUs, gloo on CPU).
     Returns the concatenation in rank order."""
@@ -58,4 +89,4 @@ def sharded_transform(ctx, input_map, output_map, parameters, key, rank, world, 
                                  shard_count=world)
 
 
-__all__ = ["shard_range", "all_gather_bytes", "sharded_msm", "sharded_transform", "_lib"]
+__all__ = ["shard_range", "bind_to_gpu_numa", "all_gather_bytes", "sharded_msm", "sharded_transform", "_lib"]
