@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """A clean checkout has no built artefacts (*.so are git-ignored): build the C-ABI library and the oracle once."""
+    lib_path = os.path.join(ROOT, "phase2_bn254_b200", "libp2b.so")
+    if not os.path.exists(lib_path):
+        import subprocess
+        subprocess.check_call([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle as oc
