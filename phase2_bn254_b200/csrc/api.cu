@@ -65,6 +65,7 @@ int ctx_collect_error(Ctx *c) {
     P2B_CUDA(c, cudaStreamSynchronize(c->copy_out));
     unsigned long long e = *c->h_err;
     if (e == ERR_NONE) return P2B_OK;
+    cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream);   // a reported error never leaks into later calls
     int kind = (int)((e >> 4) & 0xf), sub = (int)(e & 0xf);
     c->err_index = e >> 8;
     c->err_sub = sub;

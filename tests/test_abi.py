@@ -95,3 +95,16 @@ def test_params_layout_host_logic():
         params_layout(buf + b"x")
     with pytest.raises(ValueError):
         params_layout(buf[:-1])
+
+
+def test_size_helpers_and_null_ctx():
+    from phase2_bn254_b200 import lib
+    so = lib.load()
+    for m in (0, 1, 10, 20):
+        assert so.p2b_pot_radix_file_size(m) == 192 + 384 * (1 << m)          # prepare_phase2.rs:158-240 layout
+    import ctypes
+    for name in ("p2b_g1_group_fft", "p2b_pot_prepare_phase2", "p2b_pot_decompress", "p2b_g2_recode", "p2b_fr_fft", "p2b_sync"):
+        fn = getattr(so, name)
+        fn.restype = ctypes.c_int
+        nargs = len(fn.argtypes)
+        assert fn(*([None] + [0] * (nargs - 1))) == lib.EARG, name
