@@ -287,11 +287,12 @@ def run_ours(args, rank, world, local_rank):
     acc_ms, acc_k = prof["accumulate"]
     acc_avg_ms = acc_ms / max(1, args.steps)       # the accumulation of one MSM (one launch per window group)
     achieved = 96.0 * n / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms else None
-    traffic = pipe_busy = None
+    traffic = pipe_busy = mul_peak = None
     try:
         prof_json = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = prof_json.get("k_msm_accumulate<Fq>@2^%d" % args.log_n)
         pipe_busy = prof_json.get("k_msm_accumulate<Fq>@2^%d:fmaheavy_busy" % args.log_n)
+        mul_peak = prof_json.get("mont_mul_peak_gmul_per_s")
     except (OSError, ValueError):
         pass
     line = {
@@ -314,6 +315,13 @@ def run_ours(args, rank, world, local_rank):
                      "note": "bound by the integer multiplier pipe, not by HBM (see DESIGN.md section 4); traffic = DRAM bytes "
                              "of the accumulation of one MSM from the ncu capture; kernel time / step time = %.2f (the "
                              "sort of the next window group runs concurrently)" % (acc_avg_ms / dev_ms if dev_ms else 0)},
+        # the roofline that actually binds: Montgomery multiplications per second against the measured multiplier ceiling
+        # (tools/imad_bench.cu, profiles/r1_imad_microbench.txt); one XYZZ mixed add = 10 field multiplications, and the
+        # accumulation performs one per (term, window): 15 windows of 17 bits at 2^26 (csrc/msm_impl.cuh msm_geometry)
+        "compute_roofline": (lambda nw: {"unit": "G field-mul/s", "achieved": round(10.0 * nw * n / (acc_avg_ms * 1e-3) / 1e9, 2),
+                                         "peak": mul_peak, "frac": round(10.0 * nw * n / (acc_avg_ms * 1e-3) / 1e9 / mul_peak, 4)
+                                         if mul_peak else None, "windows": nw, "peak_source": "measured microbenchmark"})(
+            {20: 17, 21: 17, 22: 16, 23: 16, 24: 15, 25: 15, 26: 15, 27: 14, 28: 14}.get(args.log_n, 15)) if acc_avg_ms else None,
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
         "result_x": result["r"][:32].hex(),
     }
