@@ -156,10 +156,7 @@ static int host_batch(Ctx *c, int g2, const uint8_t *in, uint8_t *out, size_t n,
     HostJob j;
     memset(&j, 0, sizeof j);
     j.g2 = g2; j.in = in; j.out = out; j.n = n; j.in_enc = in_enc; j.out_enc = out_enc; j.flags = flags;
-    if (n_scalars == 1 && n != 1) {
-        j.sc.mode = 1;
-        if (!read_scalar_be(scalars, j.sc.k)) return ctx_fail(c, P2B_EARG, "scalar not canonical");
-    } else if (n_scalars == 1) {
+    if (n_scalars == 1) {
         j.sc.mode = 1;
         if (!read_scalar_be(scalars, j.sc.k)) return ctx_fail(c, P2B_EARG, "scalar not canonical");
     } else {

@@ -409,7 +409,8 @@ template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(C
     }
     // odd-multiples table (G1) + double-buffered point / scalar tiles + 2 mbarriers
     const size_t smem = TablePolicy<F, BLOCK>::TABLE_BYTES + 2 * (size_t)BLOCK * (Wire<F>::WORDS_UNCOMPRESSED * 4 + 32) + 16;
-    static bool attr_set = false;
+    static bool attr_done[64] = {};          // function attributes are per device
+    bool &attr_set = attr_done[c->device & 63];
     if (!attr_set && smem) {
         P2B_CUDA(c, cudaFuncSetAttribute(k_batch_mul<F, BLOCK, GLV, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (TablePolicy<F, BLOCK>::TABLE_BYTES)

@@ -226,7 +226,8 @@ static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
 }
 
 template <bool FIRST, bool LAST> static int fft_launch_pass(Ctx *c, const FftPass &p, uint32_t blocks, size_t smem) {
-    static bool attr = false;
+    static bool attr_done[64] = {};          // function attributes are per device
+    bool &attr = attr_done[c->device & 63];
     if (!attr) {
         P2B_CUDA(c, cudaFuncSetAttribute(k_fft_pass<FIRST, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr = true;
