@@ -4,7 +4,6 @@
 namespace p2b {
 int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire, size_t geom_n,
                  int phase, uint64_t err_base);
-void launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
 
 // result: uncompressed wire bytes in device memory c->misc (first 128 bytes)
 static int msm_run(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, uint8_t *out_host) {
@@ -97,8 +96,8 @@ static int sum_points(Ctx *c, int g2, const uint8_t *points, size_t count, uint8
     if ((rc = dev_reserve(c, c->misc, 4096 + count * psz))) return rc;
     uint32_t *d_out = (uint32_t *)c->misc.p, *d_in = d_out + 1024;
     if (count) P2B_CUDA(c, cudaMemcpyAsync(d_in, points, count * psz, cudaMemcpyHostToDevice, c->stream));
-    if (g2) launch_sum_points_g2(c, d_in, (uint32_t)count, d_out);
-    else k_sum_points<Fq><<<1, 32, 0, c->stream>>>(d_in, (uint32_t)count, d_out, c->d_err);
+    if (g2) msm_launch_sum_points_g2(c, d_in, (uint32_t)count, d_out);
+    else msm_launch_sum_points_g1(c, d_in, (uint32_t)count, d_out);
     c->launches++;
     P2B_CUDA(c, cudaMemcpyAsync(out, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
     return ctx_collect_error(c);

@@ -6,7 +6,4 @@ int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, 
                  int phase, uint64_t err_base) {
     return msm_typed<Fq2>(c, d_points, d_scalars, n, d_out_wire, geom_n, phase, err_base);
 }
-void launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out) {
-    k_sum_points<Fq2><<<1, 32, 0, c->stream>>>(d_in, count, d_out, c->d_err);
-}
 }  // namespace p2b

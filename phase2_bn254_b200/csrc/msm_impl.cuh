@@ -408,6 +408,25 @@ template <class F> __global__ void k_sum_points(const uint32_t *wire, uint32_t c
 }
 
 // ------------------------------------------------------------------------------------------------- host side
+// The heavy-bucket and reduction kernels are compiled in their own translation units (msm_g{1,2}_heavy.cu,
+// msm_g{1,2}_reduce.cu) so that the library builds in parallel; these are their launchers.
+template <class F> void msm_launch_heavy_impl(Ctx *c, const uint32_t *aff, const uint32_t *sorted, uint32_t *buckets, const MsmHeavy &hv) {
+    k_msm_heavy<F><<<c->sm_count * 4, 128, 0, c->stream>>>(aff, sorted, hv);
+    k_msm_heavy_combine<F><<<8, 128, 0, c->stream>>>(buckets, hv);
+}
+template <class F> void msm_launch_reduce_impl(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uint32_t *s1, uint32_t *s2, uint32_t *wsum,
+                                               uint32_t *d_out_wire, size_t nred) {
+    k_msm_reduce1<F><<<(int)((nred + 127) / 128), 128, 0, c->stream>>>(buckets, g, s1, s2);
+    k_msm_reduce2<F><<<g.nwin, 256, 0, c->stream>>>(s1, s2, g, wsum);
+    k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
+}
+void msm_launch_heavy_g1(Ctx *c, const uint32_t *aff, const uint32_t *sorted, uint32_t *buckets, const MsmHeavy &hv);
+void msm_launch_heavy_g2(Ctx *c, const uint32_t *aff, const uint32_t *sorted, uint32_t *buckets, const MsmHeavy &hv);
+void msm_launch_reduce_g1(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uint32_t *s1, uint32_t *s2, uint32_t *wsum, uint32_t *d_out_wire, size_t nred);
+void msm_launch_reduce_g2(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uint32_t *s1, uint32_t *s2, uint32_t *wsum, uint32_t *d_out_wire, size_t nred);
+void msm_launch_sum_points_g1(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
+void msm_launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
+
 // Window geometry.  The 255 bits (r < 2^254 plus one bit of head-room for the signed-digit carry) are split into nwin
 // windows whose widths differ by at most one bit -- a short top window would put n / 2^bits terms into each of a few
 // buckets and serialise them on a few threads (profiles/r1a/msm_c_sweep.log: 165 s at 2^26 with a 2-bit top window).
@@ -516,8 +535,8 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
         P2B_CUDA(c, cudaMemsetAsync(hv.counters, 0, 8, C));
         k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt, hv, c->d_err);
-        k_msm_heavy<F><<<c->sm_count * 4, 128, 0, C>>>(aff, sorted, hv);
-        k_msm_heavy_combine<F><<<8, 128, 0, C>>>(buckets, hv);
+        if constexpr (W == 8) msm_launch_heavy_g1(c, aff, sorted, buckets, hv);
+        else msm_launch_heavy_g2(c, aff, sorted, buckets, hv);
         prof_end(c, P2B_PROF_MSM_ACCUMULATE, 3);
         c->launches += 6;
     }
@@ -526,9 +545,8 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         return P2B_OK;
     }
     prof_begin(c, P2B_PROF_MSM_REDUCE);
-    k_msm_reduce1<F><<<(int)((nred + 127) / 128), 128, 0, c->stream>>>(buckets, g, s1, s2);
-    k_msm_reduce2<F><<<g.nwin, 256, 0, c->stream>>>(s1, s2, g, wsum);
-    k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
+    if constexpr (W == 8) msm_launch_reduce_g1(c, buckets, g, s1, s2, wsum, d_out_wire, nred);
+    else msm_launch_reduce_g2(c, buckets, g, s1, s2, wsum, d_out_wire, nred);
     prof_end(c, P2B_PROF_MSM_REDUCE, 3);
     c->launches += 3;
     P2B_CUDA(c, cudaGetLastError());
