@@ -346,6 +346,24 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "one Pippenger MSM over 2^%d of the workload's terms (%.1f s), oracle/p2b_oracle.c "
                                               "= C restatement of bellman multiexp on all host threads" % (args.ref_log_n, dt)}
+            if "extras" in line:    # the CPU restatement of the other paths, bounded samples, same host cores
+                import numpy as np
+                import oracle as oc
+                other = {}
+                for grp, gen, lg in ((0, G1_GEN, 15), (1, G2_GEN, 13)):
+                    m = 1 << lg
+                    t0 = time.perf_counter()
+                    oc.batch_mul_powers(grp, gen * m, be(TAU), None, 1, 0, 1, threads=cores)
+                    dtc = time.perf_counter() - t0
+                    other["g%d_batch_exp_2^%d" % (grp + 1, lg)] = {"s": round(dtc, 3), "Mmul_per_s": round(m / dtc / 1e6, 4)}
+                xs = np.random.default_rng(3).integers(0, 256, size=(1 << 20, 32), dtype=np.uint8)
+                xs[:, 0] &= 0x1f
+                xs = xs.tobytes()
+                t0 = time.perf_counter()
+                oc.fr_fft(xs, threads=cores)
+                dtc = time.perf_counter() - t0
+                other["fr_fft_2^20"] = {"s": round(dtc, 3), "Melem_per_s": round((1 << 20) / dtc / 1e6, 3)}
+                line["cpu_baseline"]["other_paths"] = other
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
