@@ -140,6 +140,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- GPU workload
+def msm_windows(log_n):
+    """Number of windows csrc/msm_impl.cuh msm_geometry() uses for 2^log_n terms (for the field-multiplication count)."""
+    target = max(6, min(20, int(0.6 * log_n + 3.5)))
+    for c in range(target, 1, -1):
+        nwin = (255 + c - 1) // c
+        if (255 + nwin - 1) // nwin == c:
+            return nwin
+    return 15
+
+
 def make_scalars(torch, n, seed, device):
     """n x 32 BE bytes: uniform 254-bit values folded into [0, r) (values >= r get their top nibble cleared)."""
     rbytes = torch.tensor(list(be(R_MOD)), dtype=torch.int16, device=device)
@@ -317,11 +327,11 @@ def run_ours(args, rank, world, local_rank):
                              "sort of the next window group runs concurrently)" % (acc_avg_ms / dev_ms if dev_ms else 0)},
         # the roofline that actually binds: Montgomery multiplications per second against the measured multiplier ceiling
         # (tools/imad_bench.cu, profiles/r1_imad_microbench.txt); one XYZZ mixed add = 10 field multiplications, and the
-        # accumulation performs one per (term, window): 15 windows of 17 bits at 2^26 (csrc/msm_impl.cuh msm_geometry)
+        # accumulation performs one per (term, window): 14 windows of 18-19 bits at 2^26 (csrc/msm_impl.cuh msm_geometry)
         "compute_roofline": (lambda nw: {"unit": "G field-mul/s", "achieved": round(10.0 * nw * n / (acc_avg_ms * 1e-3) / 1e9, 2),
                                          "peak": mul_peak, "frac": round(10.0 * nw * n / (acc_avg_ms * 1e-3) / 1e9 / mul_peak, 4)
                                          if mul_peak else None, "windows": nw, "peak_source": "measured microbenchmark"})(
-            {20: 17, 21: 17, 22: 16, 23: 16, 24: 15, 25: 15, 26: 15, 27: 14, 28: 14}.get(args.log_n, 15)) if acc_avg_ms else None,
+            msm_windows(args.log_n)) if acc_avg_ms else None,
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
         "result_x": result["r"][:32].hex(),
     }

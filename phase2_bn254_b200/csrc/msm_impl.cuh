@@ -183,6 +183,53 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scal
     }
 }
 
+// Buckets are handed to the accumulation threads in order of decreasing size: the 32 lanes of a warp then walk lists of
+// (almost) equal length -- with one thread per bucket the warp otherwise waits for its longest list (Poisson spread: +6 %
+// at 1024 terms per bucket, +17 % at 128) -- and the longest buckets start first.  Counting sort of the bucket sizes,
+// capped at the per-thread segment length.
+static __global__ void __launch_bounds__(256) k_msm_size_hist(const uint32_t *offsets, uint32_t slot_cnt, uint32_t cap, uint32_t *size_hist) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slot_cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t sz = offsets[i + 1] - offsets[i];
+        atomicAdd(&size_hist[sz < cap ? sz : cap], 1u);
+    }
+}
+// single block: start position of every size class, largest first; also resets the histogram for the next group
+static __global__ void __launch_bounds__(1024) k_msm_size_scan(uint32_t *size_hist, uint32_t *size_start, uint32_t nbins) {
+    __shared__ uint32_t sums[1024];
+    const uint32_t t = threadIdx.x, per = (nbins + 1023) / 1024;
+    // thread t owns the descending range of bins [hi_bin - per*(t+1) + 1 .. hi_bin - per*t], hi_bin = nbins - 1
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t r = t * per + k;                        // rank in descending order
+        if (r < nbins) s += size_hist[nbins - 1 - r];
+    }
+    sums[t] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t v = t >= d ? sums[t - d] : 0;
+        __syncthreads();
+        sums[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? sums[t - 1] : 0;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t r = t * per + k;
+        if (r < nbins) {
+            const uint32_t b = nbins - 1 - r, cnt = size_hist[b];
+            size_start[b] = run;
+            size_hist[b] = 0;
+            run += cnt;
+        }
+    }
+}
+static __global__ void __launch_bounds__(256) k_msm_size_scatter(const uint32_t *offsets, uint32_t slot_cnt, uint32_t cap, uint32_t *size_start,
+                                                                 uint32_t *perm) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slot_cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t sz = offsets[i + 1] - offsets[i];
+        perm[atomicAdd(&size_start[sz < cap ? sz : cap], 1u)] = i;
+    }
+}
+
 // Skewed inputs (many equal digits) would put most terms of a window into one bucket and serialise them on one thread.
 // A bucket thread therefore takes at most `seg` entries; the rest is cut into items of `chunk` entries that whole blocks
 // reduce (k_msm_heavy) and a last kernel folds into the bucket (k_msm_heavy_combine).  Uniform scalars never overflow
@@ -213,9 +260,12 @@ template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc
 #endif
 template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
                                                                            MsmGeom g, uint32_t *buckets, int first, uint32_t slot_lo,
-                                                                           uint32_t slot_cnt, MsmHeavy hv, unsigned long long *err) {
-    // slots [slot_lo, slot_lo + slot_cnt) = the (window, bucket) pairs of one window group; `offsets` is that group's table
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < slot_cnt; idx += gridDim.x * blockDim.x) {
+                                                                           uint32_t slot_cnt, MsmHeavy hv, unsigned long long *err,
+                                                                           const uint32_t *perm) {
+    // slots [slot_lo, slot_lo + slot_cnt) = the (window, bucket) pairs of one window group; `offsets` is that group's table;
+    // perm lists the group's slots by decreasing size
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < slot_cnt; t += gridDim.x * blockDim.x) {
+        const uint32_t idx = perm[t];
         const uint32_t gb = slot_lo + idx;
         const uint32_t lo = offsets[idx], hi = offsets[idx + 1];
         Xyzz<F> acc = xyzz_infinity<F>();
@@ -431,13 +481,13 @@ void msm_launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint
 // windows whose widths differ by at most one bit -- a short top window would put n / 2^bits terms into each of a few
 // buckets and serialise them on a few threads (profiles/r1a/msm_c_sweep.log: 165 s at 2^26 with a 2-bit top window).
 // The narrow windows (twice the load per bucket, half the buckets) come first so that their longer threads start first.
-// Width: the widest c <= 0.55 log2(n) + 4.2 that is minimal for its window count -- a fit to the sweeps on B200
-// (2^20 -> 15, 2^22 -> 16, 2^24 and 2^26 -> 17): more windows cost n mixed adds each, wider windows leave fewer terms per
-// bucket (warp-level imbalance, one thread per bucket) and lengthen the serial strip walk of the bucket reduction.
+// Width: the widest c <= 0.6 log2(n) + 3.5 that is minimal for its window count -- a fit to the sweeps on B200 with
+// size-ordered buckets (2^20 -> 15, 2^22 -> 16, 2^24 -> 17, 2^26 -> 19): more windows cost n mixed adds each, wider windows
+// lengthen the serial strip walk of the bucket reduction and leave the accumulation threads shorter lists.
 static inline MsmGeom msm_geometry(size_t n) {
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int target = (int)(0.55 * lg + 4.2);
+    int target = (int)(0.6 * lg + 3.5);
     if (const char *e = getenv("P2B_MSM_C")) {      // tuning override (results do not depend on the geometry)
         int v = atoi(e);
         if (v >= 2 && v <= 22) target = v;
@@ -475,16 +525,18 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     int rc;
     // msm_a: affine Montgomery points ; msm_b: hist | offsets | cursor ; msm_c: sorted entries ; msm_d: buckets | s1 | s2 | wsum
     if ((rc = dev_reserve(c, c->msm_a, cap_n * WU * 4))) return rc;
-    if ((rc = dev_reserve(c, c->msm_b, (3 * nslots + 16) * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_b, (4 * nslots + 16) * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * cap_n * 4))) return rc;
     const size_t nred = (size_t)g.nwin * g.tpw;
     if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin) * xy))) return rc;
     uint32_t *aff = (uint32_t *)c->msm_a.p;
     uint32_t *hist = (uint32_t *)c->msm_b.p, *cursor = hist + nslots, *offsets = cursor + nslots;   // offsets: nslots + one per group
+    uint32_t *perm = offsets + nslots + 16;
     uint32_t *sorted = (uint32_t *)c->msm_c.p;
     uint32_t *buckets = (uint32_t *)c->msm_d.p, *s1 = buckets + nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
     // overflow handling for skewed digit distributions (see MsmHeavy)
     MsmHeavy hv;
+    uint32_t *size_hist = nullptr, *size_start = nullptr;
     {
         const size_t load = cap_n / g.nb + 1;                 // average terms per bucket of a wide window
         hv.seg = (uint32_t)(8 * load < 256 ? 256 : 8 * load);
@@ -496,8 +548,11 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         const size_t total = (size_t)g.nwin * cap_n;
         hv.cap_items = (uint32_t)(total / hv.chunk + total / hv.seg + 16);
         hv.cap_buckets = (uint32_t)(total / hv.seg + 16);
-        if ((rc = dev_reserve(c, c->msm_e, 64 + ((size_t)hv.cap_items + hv.cap_buckets) * 16 + (size_t)hv.cap_items * xy))) return rc;
+        const size_t heavy_bytes = 64 + ((size_t)hv.cap_items + hv.cap_buckets) * 16 + (size_t)hv.cap_items * xy;
+        if ((rc = dev_reserve(c, c->msm_e, heavy_bytes + 2 * ((size_t)hv.seg + 2) * 4 + 64))) return rc;
         char *hp = (char *)c->msm_e.p;
+        size_hist = (uint32_t *)(hp + ((heavy_bytes + 15) & ~(size_t)15));
+        size_start = size_hist + hv.seg + 2;
         hv.counters = (uint32_t *)hp;
         hv.items = (uint4 *)(hp + 64);
         hv.hbuckets = hv.items + hv.cap_items;
@@ -517,6 +572,7 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     }
     prof_begin(c, P2B_PROF_MSM_SORT, S);
     P2B_CUDA(c, cudaMemsetAsync(hist, 0, nslots * 4, S));
+    P2B_CUDA(c, cudaMemsetAsync(size_hist, 0, ((size_t)hv.seg + 2) * 4, S));
     k_msm_prepare<F><<<grid, 256, 0, S>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
     c->launches++;
     for (uint32_t gi = 0; gi < ngroups; gi++) {
@@ -526,6 +582,12 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         k_msm_hist<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base, w_lo, w_hi);
         k_msm_scan<<<1, 1024, 0, S>>>(hist + slot_lo, offs, cursor + slot_lo, slot_cnt, (uint32_t)((size_t)w_lo * cap_n));
         k_msm_scatter<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, cursor, sorted, w_lo, w_hi);
+        {   // order the group's buckets by size (see k_msm_size_hist)
+            const int sgrid = (int)((slot_cnt + 255) / 256) < c->sm_count * 8 ? (int)((slot_cnt + 255) / 256) : c->sm_count * 8;
+            k_msm_size_hist<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_hist);
+            k_msm_size_scan<<<1, 1024, 0, S>>>(size_hist, size_start, hv.seg + 1);
+            k_msm_size_scatter<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_start, perm + slot_lo);
+        }
         if (gi + 1 == ngroups) prof_end(c, P2B_PROF_MSM_SORT, (int)(1 + 3 * ngroups), S);
         if (S != C) {
             P2B_CUDA(c, cudaEventRecord(c->msm_ev[1 + gi], S));
@@ -534,11 +596,12 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         const int agrid = (int)((slot_cnt + 127) / 128);
         prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
         P2B_CUDA(c, cudaMemsetAsync(hv.counters, 0, 8, C));
-        k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt, hv, c->d_err);
+        k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt, hv, c->d_err,
+                                                  perm + slot_lo);
         if constexpr (W == 8) msm_launch_heavy_g1(c, aff, sorted, buckets, hv);
         else msm_launch_heavy_g2(c, aff, sorted, buckets, hv);
         prof_end(c, P2B_PROF_MSM_ACCUMULATE, 3);
-        c->launches += 6;
+        c->launches += 9;
     }
     if (!(phase & MSM_LAST)) {
         P2B_CUDA(c, cudaGetLastError());

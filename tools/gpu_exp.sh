@@ -1,6 +1,5 @@
 #!/bin/bash
-set -x
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-echo "=== main"; python tools/probe.py 20 22 2>&1 | grep G1
-echo "=== variant (G1 128x3 + carveout)"; P2B_LIB=$PWD/phase2_bn254_b200/libp2b_v.so python tools/probe.py 20 22 2>&1 | grep -E "G1"
+python -m pytest tests/test_gpu_msm.py tests/test_gpu_golden.py -m gpu -x -q 2>&1 | tail -3
+echo "=== default rule"; MSM=20,22,24,26 python tools/probe.py 16 2>&1 | grep MSM
+for c in 15 16 17; do echo "== c=$c"; P2B_MSM_C=$c MSM=20,22 python tools/probe.py 16 2>&1 | grep MSM; done
+for c in 16 17 19 20; do echo "== c=$c"; P2B_MSM_C=$c MSM=24,26 python tools/probe.py 16 2>&1 | grep MSM; done
