@@ -3,14 +3,14 @@
 
 namespace p2b {
 int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire, size_t geom_n,
-                 int phase, uint64_t err_base);
+                 int phase, uint64_t err_base, size_t total_n);
 
 // result: uncompressed wire bytes in device memory c->misc (first 128 bytes)
 static int msm_run(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, uint8_t *out_host) {
     int rc;
     if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
     uint32_t *d_out = (uint32_t *)c->misc.p;
-    rc = g2 ? msm_typed_g2(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0)
+    rc = g2 ? msm_typed_g2(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0, 0)
             : msm_typed<Fq>(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0);
     if (rc) return rc;
     P2B_CUDA(c, cudaMemcpyAsync(out_host, d_out, g2 ? 128 : 64, cudaMemcpyDeviceToHost, c->stream));
@@ -58,7 +58,7 @@ static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_
         P2B_CUDA(c, cudaEventRecord(ev_in[b], c->copy_in));
         P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
         const int phase = (ci == 0 ? MSM_FIRST : 0) | (off + m == n ? MSM_LAST : 0);
-        rc = g2 ? msm_typed_g2(c, d_pts, d_sc, m, d_out, chunk, phase, off) : msm_typed<Fq>(c, d_pts, d_sc, m, d_out, chunk, phase, off);
+        rc = g2 ? msm_typed_g2(c, d_pts, d_sc, m, d_out, chunk, phase, off, n) : msm_typed<Fq>(c, d_pts, d_sc, m, d_out, chunk, phase, off, n);
         if (rc) return rc;
         P2B_CUDA(c, cudaEventRecord(ev_done[b], c->stream));
         off += m;

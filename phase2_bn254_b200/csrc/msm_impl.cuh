@@ -510,14 +510,16 @@ static inline MsmGeom msm_geometry(size_t n) {
     return g;
 }
 
-// One MSM, or one chunk of a streamed MSM: `geom_n` (>= n) fixes the window geometry and the scratch sizes for all chunks;
+// One MSM, or one chunk of a streamed MSM: `geom_n` (>= n) fixes the scratch sizes for all chunks;
 // MSM_FIRST starts fresh buckets, MSM_LAST runs the bucket / window reduction and writes the affine result.
 enum { MSM_FIRST = 1, MSM_LAST = 2 };
 template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire,
-                                 size_t geom_n, int phase, uint64_t err_base) {
+                                 size_t geom_n, int phase, uint64_t err_base, size_t total_n = 0) {
     constexpr int W = FieldTraits<F>::WORDS, WU = Wire<F>::WORDS_UNCOMPRESSED;
     if (geom_n >= ((size_t)1 << 31) || n > geom_n) return ctx_fail(c, P2B_EARG, "msm: chunk must be < 2^31 terms");
-    MsmGeom g = msm_geometry(geom_n ? geom_n : 1);
+    // window widths follow the size of the WHOLE sum (total_n, when this call is one chunk of a streamed MSM); the scratch
+    // buffers are sized for the largest chunk (geom_n)
+    MsmGeom g = msm_geometry(total_n ? total_n : (geom_n ? geom_n : 1));
     const size_t cap_n = geom_n ? geom_n : 1;
     if ((uint64_t)g.nwin * cap_n >= (1ull << 32)) return ctx_fail(c, P2B_EARG, "msm: too many terms for one pass (use the host entry point, which streams)");
     const size_t nslots = (size_t)g.nwin * g.nbk;
