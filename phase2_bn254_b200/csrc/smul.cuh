@@ -323,9 +323,10 @@ struct UniformDigits {
     int8_t d1[136], d2[136];
     int len;
 };
-template <int N> P2B_HD int wnaf5_recode(int8_t *out, uint32_t *m) {      // m: N-word magnitude, destroyed
+// m: N-word magnitude (< 2^(NDIG - 2)), destroyed; out: NDIG digits
+template <int N, int NDIG> P2B_HD int wnaf5_recode(int8_t *out, uint32_t *m) {
     int len = 0;
-    for (int i = 0; i < 32 * N + 1; i++) {
+    for (int i = 0; i < NDIG; i++) {
         int8_t d = 0;
         if (m[0] & 1u) {
             int v = (int)(m[0] & 31u);
@@ -350,7 +351,7 @@ P2B_HD UniformDigits uniform_digits(const uint32_t k[8]) {
     UniformDigits u;
     uint32_t m1[6] = {s.k1[0], s.k1[1], s.k1[2], s.k1[3], s.k1[4], 0}, m2[6] = {s.k2[0], s.k2[1], s.k2[2], s.k2[3], s.k2[4], 0};
     for (int i = 0; i < 136; i++) { u.d1[i] = 0; u.d2[i] = 0; }
-    int l1 = wnaf5_recode<5>(u.d1, m1), l2 = wnaf5_recode<5>(u.d2, m2);
+    int l1 = wnaf5_recode<6, 136>(u.d1, m1), l2 = wnaf5_recode<6, 136>(u.d2, m2);   // |k1|, |k2| < 2^132
     if (s.neg1) for (int i = 0; i < l1; i++) u.d1[i] = (int8_t)-u.d1[i];
     if (s.neg2) for (int i = 0; i < l2; i++) u.d2[i] = (int8_t)-u.d2[i];
     u.len = l1 > l2 ? l1 : l2;
