@@ -578,7 +578,10 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     k_msm_prepare<F><<<grid, 256, 0, S>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
     c->launches++;
     for (uint32_t gi = 0; gi < ngroups; gi++) {
-        const uint32_t w_lo = g.nwin * gi / ngroups, w_hi = g.nwin * (gi + 1) / ngroups;
+        // the first group is small: its sort is the only one that cannot hide behind an accumulation
+        const uint32_t first_hi = g.nwin / 7 ? g.nwin / 7 : 1;
+        const uint32_t bounds[4] = {0, ngroups == 3 ? first_hi : g.nwin, ngroups == 3 ? (g.nwin + first_hi) / 2 : g.nwin, g.nwin};
+        const uint32_t w_lo = bounds[gi], w_hi = ngroups == 3 ? bounds[gi + 1] : g.nwin;
         const uint32_t slot_lo = w_lo * g.nbk, slot_cnt = (w_hi - w_lo) * g.nbk;
         uint32_t *offs = offsets + slot_lo + gi;
         k_msm_hist<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base, w_lo, w_hi);
