@@ -27,7 +27,7 @@ static int msm_begin(Ctx *c) {
 // Host buffers larger than STREAM_MIN terms are streamed: chunks of up to STREAM_CHUNK terms are copied on the H2D stream into
 // a double-buffered staging area while the previous chunk is sorted and accumulated into the SAME buckets; the bucket
 // reduction runs once at the end.  The sum is unchanged (bucket contents are sums of the same terms).
-static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 25;
+static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 24;
 static size_t msm_stream_chunk() {       // P2B_MSM_STREAM_CHUNK=<terms>: test hook to exercise the streamed path at small sizes
     const char *e = getenv("P2B_MSM_STREAM_CHUNK");
     long v = e ? atol(e) : 0;

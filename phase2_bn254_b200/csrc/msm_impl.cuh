@@ -7,7 +7,7 @@
 //
 //   k_msm_prepare     wire points -> affine Montgomery (AoS, 64/128 B), once per call
 //   k_msm_hist        signed c-bit digits of every scalar; histogram of (window, |digit|) with L2 atomics
-//   k_msm_scan        exclusive prefix sum of the histogram -> bucket offsets (counting sort, pass 2)
+//   k_msm_scan_*      exclusive prefix sum of the histogram -> bucket offsets (counting sort, pass 2)
 //   k_msm_scatter     digits recomputed; (point index, sign) written to its bucket's slot (counting sort, pass 3)
 //   k_msm_accumulate  one thread per bucket: gathers its points (coalescing is impossible by construction; every
 //                     gather is a full 64/128 B point), mixed adds in XYZZ coordinates (8M + 2S)
@@ -144,24 +144,49 @@ static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars
     }
 }
 
-// single block: exclusive scan of `count` entries; also copies the offsets into `cursor`
-static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t count, uint32_t base) {
-    __shared__ uint32_t sums[1024];
-    const uint32_t t = threadIdx.x, per = (count + 1023) / 1024;
-    const uint32_t lo = t * per, hi = lo + per < count ? lo + per : count;
-    uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += hist[i];
-    sums[t] = s;
+// Exclusive prefix sum of the histogram -> bucket offsets (also copied into `cursor`), offsets[count] = base + total.
+// Three small kernels: per-tile sums (4096 entries per block), a serial scan of the <= 2k tile sums, per-tile rescan.
+static constexpr uint32_t SCAN_TILE = 4096;     // 256 threads x 16 entries
+static __device__ __forceinline__ uint32_t block_sum_256(uint32_t v, uint32_t *sm) {      // returns the block total to all
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
     __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        uint32_t v = t >= d ? sums[t - d] : 0;
-        __syncthreads();
-        sums[t] += v;
-        __syncthreads();
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) t += sm[w];
+    __syncthreads();
+    return t;
+}
+static __global__ void __launch_bounds__(256) k_msm_scan_tiles(const uint32_t *hist, uint32_t count, uint32_t *tile_sums) {
+    __shared__ uint32_t sm[8];
+    const uint32_t lo = blockIdx.x * SCAN_TILE + threadIdx.x * 16;
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < 16; k++) s += lo + k < count ? hist[lo + k] : 0u;
+    s = block_sum_256(s, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
+}
+static __global__ void k_msm_scan_tops(uint32_t *tile_sums, uint32_t ntiles, uint32_t base) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t run = base;
+    for (uint32_t i = 0; i < ntiles; i++) { const uint32_t v = tile_sums[i]; tile_sums[i] = run; run += v; }
+    tile_sums[ntiles] = run;
+}
+static __global__ void __launch_bounds__(256) k_msm_scan_apply(const uint32_t *hist, uint32_t *offsets, uint32_t *cursor, uint32_t count,
+                                                               const uint32_t *tile_sums, uint32_t ntiles) {
+    __shared__ uint32_t warp_tot[8];
+    const uint32_t lo = blockIdx.x * SCAN_TILE + threadIdx.x * 16, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t v[16], s = 0;
+    for (uint32_t k = 0; k < 16; k++) { v[k] = lo + k < count ? hist[lo + k] : 0u; s += v[k]; }
+    uint32_t incl = s;                                          // inclusive scan of the thread sums within the warp
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += o; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t run = tile_sums[blockIdx.x] + incl - s;
+    for (uint32_t w = 0; w < wid; w++) run += warp_tot[w];
+    for (uint32_t k = 0; k < 16; k++) {
+        if (lo + k < count) { offsets[lo + k] = run; cursor[lo + k] = run; }
+        run += v[k];
     }
-    uint32_t run = base + (t ? sums[t - 1] : 0);
-    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; cursor[i] = run; run += hist[i]; }
-    if (t == 1023) offsets[count] = base + sums[1023];
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[count] = tile_sums[ntiles];
 }
 
 static __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *cursor, uint32_t *sorted,
@@ -527,13 +552,13 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     int rc;
     // msm_a: affine Montgomery points ; msm_b: hist | offsets | cursor ; msm_c: sorted entries ; msm_d: buckets | s1 | s2 | wsum
     if ((rc = dev_reserve(c, c->msm_a, cap_n * WU * 4))) return rc;
-    if ((rc = dev_reserve(c, c->msm_b, (4 * nslots + 16) * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_b, (4 * nslots + 16 + nslots / SCAN_TILE + 8) * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * cap_n * 4))) return rc;
     const size_t nred = (size_t)g.nwin * g.tpw;
     if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin) * xy))) return rc;
     uint32_t *aff = (uint32_t *)c->msm_a.p;
     uint32_t *hist = (uint32_t *)c->msm_b.p, *cursor = hist + nslots, *offsets = cursor + nslots;   // offsets: nslots + one per group
-    uint32_t *perm = offsets + nslots + 16;
+    uint32_t *perm = offsets + nslots + 16, *tile_sums = perm + nslots;
     uint32_t *sorted = (uint32_t *)c->msm_c.p;
     uint32_t *buckets = (uint32_t *)c->msm_d.p, *s1 = buckets + nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
     // overflow handling for skewed digit distributions (see MsmHeavy)
@@ -585,7 +610,12 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         const uint32_t slot_lo = w_lo * g.nbk, slot_cnt = (w_hi - w_lo) * g.nbk;
         uint32_t *offs = offsets + slot_lo + gi;
         k_msm_hist<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base, w_lo, w_hi);
-        k_msm_scan<<<1, 1024, 0, S>>>(hist + slot_lo, offs, cursor + slot_lo, slot_cnt, (uint32_t)((size_t)w_lo * cap_n));
+        {
+            const uint32_t ntiles = (slot_cnt + SCAN_TILE - 1) / SCAN_TILE;
+            k_msm_scan_tiles<<<ntiles, 256, 0, S>>>(hist + slot_lo, slot_cnt, tile_sums);
+            k_msm_scan_tops<<<1, 32, 0, S>>>(tile_sums, ntiles, (uint32_t)((size_t)w_lo * cap_n));
+            k_msm_scan_apply<<<ntiles, 256, 0, S>>>(hist + slot_lo, offs, cursor + slot_lo, slot_cnt, tile_sums, ntiles);
+        }
         k_msm_scatter<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, cursor, sorted, w_lo, w_hi);
         {   // order the group's buckets by size (see k_msm_size_hist)
             const int sgrid = (int)((slot_cnt + 255) / 256) < c->sm_count * 8 ? (int)((slot_cnt + 255) / 256) : c->sm_count * 8;
@@ -606,7 +636,7 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         if constexpr (W == 8) msm_launch_heavy_g1(c, aff, sorted, buckets, hv);
         else msm_launch_heavy_g2(c, aff, sorted, buckets, hv);
         prof_end(c, P2B_PROF_MSM_ACCUMULATE, 3);
-        c->launches += 9;
+        c->launches += 11;
     }
     if (!(phase & MSM_LAST)) {
         P2B_CUDA(c, cudaGetLastError());
