@@ -600,7 +600,8 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     prof_begin(c, P2B_PROF_MSM_SORT, S);
     P2B_CUDA(c, cudaMemsetAsync(hist, 0, nslots * 4, S));
     P2B_CUDA(c, cudaMemsetAsync(size_hist, 0, ((size_t)hv.seg + 2) * 4, S));
-    k_msm_prepare<F><<<grid, 256, 0, S>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
+    // the point decode is only needed by the accumulation: it runs on the compute stream, next to the first group's sort
+    k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
     c->launches++;
     for (uint32_t gi = 0; gi < ngroups; gi++) {
         // the first group is small: its sort is the only one that cannot hide behind an accumulation
@@ -623,7 +624,7 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
             k_msm_size_scan<<<1, 1024, 0, S>>>(size_hist, size_start, hv.seg + 1);
             k_msm_size_scatter<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_start, perm + slot_lo);
         }
-        if (gi + 1 == ngroups) prof_end(c, P2B_PROF_MSM_SORT, (int)(1 + 3 * ngroups), S);
+        if (gi + 1 == ngroups) prof_end(c, P2B_PROF_MSM_SORT, (int)(8 * ngroups), S);
         if (S != C) {
             P2B_CUDA(c, cudaEventRecord(c->msm_ev[1 + gi], S));
             P2B_CUDA(c, cudaStreamWaitEvent(C, c->msm_ev[1 + gi], 0));
