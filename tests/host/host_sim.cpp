@@ -89,6 +89,13 @@ void sim_glv(const uint8_t *k_be, uint32_t *k1, uint32_t *k2, int *neg1, int *ne
     memcpy(k1, s.k1, 20); memcpy(k2, s.k2, 20);
     *neg1 = s.neg1; *neg2 = s.neg2;
 }
+// width-5 NAF recoding of the GLV halves (the uniform-scalar path): digits LSB first, returns the common length
+int sim_uniform_digits(const uint8_t *k_be, int8_t *d1, int8_t *d2) {
+    uint32_t k[8]; k_from_be(k_be, k);
+    UniformDigits u = uniform_digits(k);
+    memcpy(d1, u.d1, 136); memcpy(d2, u.d2, 136);
+    return u.len;
+}
 // field op on canonical BE operands: field 0 = Fq, 1 = Fr; op 0 mul 1 add 2 sub 3 inv 4 neg
 void sim_field(int field, int op, const uint8_t *a_be, const uint8_t *b_be, uint8_t *out_be) {
     uint32_t wa[8], wb[8], wo[8];

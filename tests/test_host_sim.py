@@ -102,3 +102,26 @@ def test_xyzz_arithmetic(sim, oracle):
     out = (ctypes.c_uint8 * 64)()
     assert sim.sim_xyzz_msm(bytes(pts), bytes(sc), n, out) == 0
     assert bytes(out) == oracle.msm(0, bytes(pts), bytes(sc), threads=4)
+
+
+def test_uniform_scalar_recoding(sim):
+    """uniform_digits (csrc/smul.cuh): sum d1[i] 2^i + lambda * sum d2[i] 2^i == k (mod r); digits are odd, |d| <= 15, and
+    non-zero digits are at least 5 positions apart (width-5 NAF); the recoding never writes past its 136-digit arrays."""
+    rng = random.Random(31)
+    ks = EDGE_SCALARS + [rng.randrange(R_MOD) for _ in range(3000)] + [R_MOD - 1 - i for i in range(50)]
+    for k in ks:
+        buf1, buf2 = (ctypes.c_int8 * 200)(), (ctypes.c_int8 * 200)()
+        for i in range(136, 200):
+            buf1[i] = buf2[i] = 77                                   # canary behind the 136 digits
+        n = sim.sim_uniform_digits(be(k), buf1, buf2)
+        assert 0 <= n <= 136
+        assert all(buf1[i] == 77 and buf2[i] == 77 for i in range(136, 200))
+        for d in (buf1, buf2):
+            last = -10
+            for i in range(136):
+                if d[i]:
+                    assert d[i] % 2 != 0 and abs(d[i]) <= 15 and i - last >= 5 and i < n
+                    last = i
+        v1 = sum(int(buf1[i]) << i for i in range(136))
+        v2 = sum(int(buf2[i]) << i for i in range(136))
+        assert (v1 + v2 * LAMBDA - k) % R_MOD == 0
