@@ -186,6 +186,35 @@ uint64_t p2b_pot_radix_file_size(uint32_t m);
 int p2b_pot_prepare_phase2(p2b_ctx *ctx, const uint8_t *accumulator, uint64_t accumulator_len, uint32_t size_log2,
                            int compressed_input, int check_input, uint32_t m, uint8_t *out, uint64_t out_len, int flags);
 
+/* ---- verifier host side: pairings, hash_to_g2, key-generation RNG (CPU code, no ctx, no GPU needed) ----
+ * The reference keeps these on the CPU too: a verification does <= 20 pairings (same_ratio,
+ * powersoftau/src/utils.rs:151-159, phase2/src/utils.rs:48-57) over pairs that merge_pairs / power_pairs
+ * (two p2b_g*_msm calls) condense from millions of points.  Points are uncompressed wire encodings, decoded
+ * CHECKED (on curve); P2B_EDECODE when one does not decode. */
+/* *is_one = (prod_i e(g1_points[i], g2_points[i]) == 1); pairs containing the point at infinity contribute 1 */
+int p2b_pairing_check(const uint8_t *g1_points, const uint8_t *g2_points, size_t n, int *is_one);
+/* same_ratio((g1_a, g1_b), (g2_a, g2_b)): e(g1_a, g2_b) == e(g1_b, g2_a); false if any point is infinity */
+int p2b_same_ratio(const uint8_t g1_a[64], const uint8_t g1_b[64], const uint8_t g2_a[128], const uint8_t g2_b[128],
+                   int *same);
+/* hash_to_g2 (powersoftau/src/utils.rs:31-45, phase2/src/utils.rs:111-122): ChaChaRng::from_seed(first 32 digest
+ * bytes as 8 big-endian u32).gen::<G2>() -- restated from rand 0.4.6 / ff_derive, which are not vendored in the
+ * reference tree; no reference vector exists for it in-tree (parity unpinned for this function). */
+int p2b_hash_to_g2(const uint8_t digest[32], uint8_t out[128]);
+/* ChaChaRng (rand 0.4.6) in a caller-owned state block, and the reference's samplers over it:
+ * Fr::rand (canonical value, 32 B big-endian), G1::rand / G2::rand (pairing/src/bn256/ec.rs:711-726,1091-1106). */
+#define P2B_RNG_STATE_BYTES 136
+int p2b_rng_seed(uint8_t state[P2B_RNG_STATE_BYTES], const uint32_t seed[8]);
+int p2b_rng_u32(uint8_t state[P2B_RNG_STATE_BYTES], uint32_t *out);
+int p2b_rng_fr(uint8_t state[P2B_RNG_STATE_BYTES], uint8_t out_be32[32]);
+int p2b_rng_g1(uint8_t state[P2B_RNG_STATE_BYTES], uint8_t out[64]);
+int p2b_rng_g2(uint8_t state[P2B_RNG_STATE_BYTES], uint8_t out[128]);
+/* one scalar multiplication on the host (keypair.rs:64-84: g1_s.mul(x), g2_s.mul(x); CurveAffine::mul_bits) */
+int p2b_host_g1_mul(const uint8_t point[64], const uint8_t scalar_be32[32], uint8_t out[64]);
+int p2b_host_g2_mul(const uint8_t point[128], const uint8_t scalar_be32[32], uint8_t out[128]);
+/* test hook: xi^((q-1)/6), its square and cube (Montgomery limbs) = FROBENIUS_COEFF_FQ12_C1[1],
+ * FROBENIUS_COEFF_FQ6_C1[1], XI_TO_Q_MINUS_1_OVER_2 of pairing/src/bn256/fq.rs */
+int p2b_pairing_constants(uint8_t out[192]);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

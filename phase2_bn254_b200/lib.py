@@ -28,6 +28,8 @@ SYMBOLS = [
     "p2b_fr_fft", "p2b_fr_fft_dev", "p2b_profile_enable", "p2b_profile_read",
     "p2b_pot_decompress", "p2b_g1_recode", "p2b_g2_recode",
     "p2b_g1_group_fft", "p2b_g2_group_fft", "p2b_pot_radix_file_size", "p2b_pot_prepare_phase2",
+    "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
+    "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -92,6 +94,15 @@ def load():
     lib.p2b_pot_radix_file_size.argtypes = [u32]
     lib.p2b_pot_radix_file_size.restype = u64
     lib.p2b_pot_prepare_phase2.argtypes = [vp, u8p, u64, u32, i32, i32, u32, u8p, u64, i32]
+    lib.p2b_pairing_check.argtypes = [u8p, u8p, sz, ctypes.POINTER(i32)]
+    lib.p2b_same_ratio.argtypes = [u8p, u8p, u8p, u8p, ctypes.POINTER(i32)]
+    lib.p2b_hash_to_g2.argtypes = [u8p, u8p]
+    lib.p2b_rng_seed.argtypes = [u8p, ctypes.POINTER(u32)]
+    lib.p2b_rng_u32.argtypes = [u8p, ctypes.POINTER(u32)]
+    for name in ("p2b_rng_fr", "p2b_rng_g1", "p2b_rng_g2", "p2b_pairing_constants"):
+        getattr(lib, name).argtypes = [u8p] * (1 if name == "p2b_pairing_constants" else 2)
+    lib.p2b_host_g1_mul.argtypes = [u8p, u8p, u8p]
+    lib.p2b_host_g2_mul.argtypes = [u8p, u8p, u8p]
     lib.p2b_profile_enable.argtypes = [vp, i32]
     lib.p2b_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     _lib = lib
@@ -113,6 +124,96 @@ def _host(buf):
 
 def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else ctypes.c_void_p(int(a))
+
+
+# ---- verifier host side (CPU code inside libp2b.so, as in the reference: pairings, hash_to_g2, key-generation RNG) ----
+def _hostcall(name, *args):
+    rc = getattr(load(), name)(*args)
+    if rc:
+        raise P2BError(rc, {EARG: "bad argument", EDECODE: "point does not decode"}.get(rc, "error") + " in " + name)
+
+
+def _fixed(buf, size, what):
+    a = _host(buf)
+    if a.size != size:
+        raise ValueError("%s must be %d bytes, got %d" % (what, size, a.size))
+    return a
+
+
+def pairing_check(g1_points, g2_points):
+    """prod_i e(P_i, Q_i) == 1 over uncompressed points (pairs with a point at infinity contribute 1)."""
+    a, b = _host(g1_points), _host(g2_points)
+    if a.size % 64 or b.size != 2 * a.size:
+        raise ValueError("need n G1 points (64 B) and n G2 points (128 B)")
+    r = ctypes.c_int(0)
+    _hostcall("p2b_pairing_check", _ptr(a), _ptr(b), a.size // 64, ctypes.byref(r))
+    return bool(r.value)
+
+
+def same_ratio(g1, g2):
+    """same_ratio((a, b), (c, d)): e(a, d) == e(b, c) (powersoftau/src/utils.rs:151-159, phase2/src/utils.rs:48-57)."""
+    a, b = _fixed(g1[0], 64, "g1.0"), _fixed(g1[1], 64, "g1.1")
+    c, d = _fixed(g2[0], 128, "g2.0"), _fixed(g2[1], 128, "g2.1")
+    r = ctypes.c_int(0)
+    _hostcall("p2b_same_ratio", _ptr(a), _ptr(b), _ptr(c), _ptr(d), ctypes.byref(r))
+    return bool(r.value)
+
+
+def hash_to_g2(digest):
+    """hash_to_g2(digest) (powersoftau/src/utils.rs:31-45): 128-byte uncompressed G2 point from the first 32 bytes."""
+    d = _host(digest)
+    if d.size < 32:
+        raise ValueError("digest must be at least 32 bytes")
+    d = np.ascontiguousarray(d[:32])
+    out = np.empty(128, dtype=np.uint8)
+    _hostcall("p2b_hash_to_g2", _ptr(d), _ptr(out))
+    return out.tobytes()
+
+
+def host_mul(group, point, scalar_be32):
+    """One scalar multiplication on the host (CurveAffine::mul of the key generation, keypair.rs:64-84)."""
+    size = 128 if group == G2 else 64
+    p, k = _fixed(point, size, "point"), _fixed(scalar_be32, 32, "scalar")
+    out = np.empty(size, dtype=np.uint8)
+    _hostcall("p2b_host_g2_mul" if group == G2 else "p2b_host_g1_mul", _ptr(p), _ptr(k), _ptr(out))
+    return out.tobytes()
+
+
+class ChaChaRng:
+    """rand 0.4.6 `ChaChaRng::from_seed(&[u32; 8])` with the reference's samplers (restated; the crate is not vendored)."""
+
+    def __init__(self, seed_words):
+        words = [int(w) & 0xffffffff for w in seed_words]
+        if len(words) != 8:
+            raise ValueError("seed is 8 u32 words")
+        self._state = np.zeros(136, dtype=np.uint8)
+        _hostcall("p2b_rng_seed", _ptr(self._state), (ctypes.c_uint32 * 8)(*words))
+
+    @classmethod
+    def from_digest(cls, digest):
+        """Seed from the first 32 bytes as 8 big-endian words (hash_to_g2, beacon_constrained.rs:81-93)."""
+        d = bytes(digest)[:32]
+        return cls([int.from_bytes(d[4 * i: 4 * i + 4], "big") for i in range(8)])
+
+    def next_u32(self):
+        v = ctypes.c_uint32(0)
+        _hostcall("p2b_rng_u32", _ptr(self._state), ctypes.byref(v))
+        return v.value
+
+    def _gen(self, name, size):
+        out = np.empty(size, dtype=np.uint8)
+        _hostcall(name, _ptr(self._state), _ptr(out))
+        return out.tobytes()
+
+    def gen_fr(self):
+        """Fr::rand as an int in [0, r)."""
+        return int.from_bytes(self._gen("p2b_rng_fr", 32), "big")
+
+    def gen_g1(self):
+        return self._gen("p2b_rng_g1", 64)
+
+    def gen_g2(self):
+        return self._gen("p2b_rng_g2", 128)
 
 
 class Context:

@@ -4,6 +4,7 @@ Mirrors  MPCParameters::{read, write, contribute}  phase2/src/parameters.rs:414-
 PublicKey wire form phase2/src/keypair.rs:50-105.  Parameters are kept in their serialized form
 (bellman/src/groth16/mod.rs:252-285): the GPU path consumes and produces wire bytes directly.
 """
+import hashlib
 import struct
 
 import numpy as np
@@ -69,11 +70,20 @@ class MPCParameters:
     def write(self, writer):
         writer.write(self.data.tobytes())
 
-    def contribute(self, delta, s_g1, r_g2=None, ctx=None, hash_to_g2=None):
+    def section(self, name):
+        """The wire bytes of one section (numpy view)."""
+        off, n, size, _ = params_layout(self.data)[name]
+        return self.data[off: off + n * size]
+
+    def contribute(self, delta=None, s_g1=None, r_g2=None, ctx=None, hash_to_g2=None, rng=None):
         """Contributes `delta` (int in [1, r)).  The reference draws delta, s = G1::rand and r = hash_to_g2(transcript)
-        from its ChaCha RNG (parameters.rs:860-908); here they are explicit: pass r_g2, or a `hash_to_g2` callable
-        mapping the 64-byte transcript to a 128-byte uncompressed G2 point.  Returns the 64-byte contribution hash."""
+        from its ChaCha RNG (parameters.rs:860-908): pass `rng` (a lib.ChaChaRng) to do the same, or make them explicit:
+        delta and s_g1 plus r_g2, or a `hash_to_g2` callable mapping the 64-byte transcript to a 128-byte uncompressed
+        G2 point.  Returns the 64-byte contribution hash."""
         ctx = ctx or _lib.Context(0)
+        if rng is not None:
+            delta, s_g1 = rng.gen_fr(), np.frombuffer(rng.gen_g1(), dtype=np.uint8)      # keypair(): delta, then s
+            hash_to_g2 = hash_to_g2 or _lib.hash_to_g2
         d = np.frombuffer(int(delta).to_bytes(32, "big"), dtype=np.uint8)
         if r_g2 is None:
             if hash_to_g2 is None:
@@ -82,3 +92,88 @@ class MPCParameters:
         out, h = ctx.phase2_contribute(self.data, d, s_g1, r_g2)
         self.data = out
         return h
+
+
+class VerificationError(Exception):
+    """The `Err(())` of verify_contribution / MPCParameters::verify, with the failed check named."""
+
+
+def merge_pairs(ctx, v1, v2, rng=None):
+    """Random linear combination (sum rho_i v1_i, sum rho_i v2_i) over G1 vectors (phase2/src/utils.rs:59-105): two MSMs."""
+    rng = rng or np.random.default_rng()
+    n = v1.size // 64
+    if n != v2.size // 64:
+        raise ValueError("merge_pairs: length mismatch")
+    if n == 0:
+        zero = bytes([0x40]) + bytes(63)
+        return zero, zero
+    rho = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    rho[:, 0] &= 0x1f                                            # < 2^253 < r
+    rho = rho.reshape(-1)
+    return ctx.msm(0, v1, rho), ctx.msm(0, v2, rho)
+
+
+def verify_contribution(before, after, ctx=None, rng=None):
+    """verify_contribution(before, after) -> the 64-byte hash of the new contribution (parameters.rs:722-855).
+    Raises VerificationError where the reference returns Err(())."""
+    ctx = ctx or _lib.Context(0)
+    lb, la = params_layout(before.data), params_layout(after.data)
+    raw = lambda m, lay, name: m.data[lay[name][0]: lay[name][0] + lay[name][1] * lay[name][2]]
+
+    def fail(what):
+        raise VerificationError(what)
+
+    nb, na = lb["contributions"][1], la["contributions"][1]
+    if na != nb + 1:
+        fail("transformation must add exactly one contribution")
+    if raw(before, lb, "contributions").tobytes() != raw(after, la, "contributions")[: nb * 384].tobytes():
+        fail("previous contributions changed")
+    for name in ("h", "l"):
+        if lb[name][1] != la[name][1]:
+            fail("%s changed length" % name)
+    for name in ("a", "b_g1", "b_g2", "alpha_g1", "beta_g1", "beta_g2", "gamma_g2", "ic", "cs_hash"):
+        if lb[name][1] != la[name][1] or raw(before, lb, name).tobytes() != raw(after, la, name).tobytes():
+            fail("%s changed" % name)
+    pk = raw(after, la, "contributions")[nb * 384:].tobytes()
+    delta_after, s, s_delta, r_delta, transcript = pk[:64], pk[64:128], pk[128:192], pk[192:320], pk[320:384]
+    h = hashlib.blake2b()
+    h.update(raw(before, lb, "cs_hash").tobytes())
+    h.update(raw(before, lb, "contributions").tobytes())
+    h.update(s)
+    h.update(s_delta)
+    if transcript != h.digest():
+        fail("transcript is inconsistent")
+    r = _lib.hash_to_g2(h.digest())
+    try:
+        if not _lib.same_ratio((s, s_delta), (r, r_delta)):                        # same_ratio((r, r_delta), (s, s_delta))
+            fail("signature of knowledge")
+        d1b, d1a = raw(before, lb, "delta_g1").tobytes(), raw(after, la, "delta_g1").tobytes()
+        d2b, d2a = raw(before, lb, "delta_g2").tobytes(), raw(after, la, "delta_g2").tobytes()
+        if not _lib.same_ratio((d1b, delta_after), (r, r_delta)):
+            fail("delta_g1 is not the old delta times the new one")
+        if delta_after != d1a:
+            fail("delta_after != delta_g1")
+        g1_one = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")
+        from .powersoftau import G2_ONE
+        if not _lib.same_ratio((g1_one, delta_after), (G2_ONE, d2a)):
+            fail("delta_g2 is inconsistent with delta_g1")
+        for name in ("h", "l"):                                                     # updated with delta^-1: ratios reversed
+            if not _lib.same_ratio(merge_pairs(ctx, raw(before, lb, name), raw(after, la, name), rng), (d2a, d2b)):
+                fail("%s query was not multiplied by delta^-1" % name)
+    except _lib.P2BError as e:
+        fail("a point does not decode: %s" % e)
+    return hashlib.blake2b(pk).digest()
+
+
+def keypair(rng, current):
+    """keypair(rng, current) -> (public key bytes [384], delta) (parameters.rs:860-908)."""
+    lay = params_layout(current.data)
+    raw = lambda name: current.data[lay[name][0]: lay[name][0] + lay[name][1] * lay[name][2]].tobytes()
+    delta = rng.gen_fr()
+    db = int(delta).to_bytes(32, "big")
+    s = rng.gen_g1()
+    s_delta = _lib.host_mul(0, s, db)
+    h = hashlib.blake2b(raw("cs_hash") + raw("contributions") + s + s_delta).digest()
+    r = _lib.hash_to_g2(h)
+    r_delta = _lib.host_mul(1, r, db)
+    return _lib.host_mul(0, raw("delta_g1"), db) + s + s_delta + r_delta + h, delta

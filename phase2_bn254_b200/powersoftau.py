@@ -6,6 +6,8 @@ Mirrors (names, argument meaning, error behaviour):
   DeserializationError   parameters.rs:143-170
   PrivateKey             powersoftau/src/keypair.rs:47-51
   BatchedAccumulator.transform   powersoftau/src/batched_accumulator.rs:1119-1292
+  BatchedAccumulator.verify_transformation   batched_accumulator.rs:279-540 (MSMs on the GPU, pairings on the host)
+  PublicKey, keypair, compute_g2_s, hash_to_g2, same_ratio   keypair.rs:29-213, utils.rs:31-45,151-185
 The maps are numpy uint8 arrays (np.memmap works), exactly the byte layout of the challenge / response files.
 """
 import hashlib
@@ -61,6 +63,90 @@ class PrivateKey:
     tau: int
     alpha: int
     beta: int
+
+
+G1_ONE = (1).to_bytes(32, "big") + (2).to_bytes(32, "big")                          # ec.rs:1013-1051
+G2_ONE = b"".join(v.to_bytes(32, "big") for v in (                                  # fq.rs:54-83 (c1 first)
+    11559732032986387107991004021392285783925812861821192530917403151452391805634,
+    10857046999023057135944570762232829481370756359578518086990519993285655852781,
+    4082367875863433681332203403145435568316851327593401208105741076214120093531,
+    8495653923123431417604973247489272438418190587263600148770280649306958101930))
+
+same_ratio = _lib.same_ratio          # utils.rs:151-159
+hash_to_g2 = _lib.hash_to_g2          # utils.rs:31-45
+
+
+def compute_g2_s(digest, g1_s, g1_s_x, personalization):
+    """Blake2b(personalization | digest | g1_s | g1_s_x) hashed into G2 (utils.rs:172-185)."""
+    h = hashlib.blake2b()
+    h.update(bytes([personalization]))
+    h.update(bytes(digest))
+    h.update(bytes(g1_s))
+    h.update(bytes(g1_s_x))
+    return hash_to_g2(h.digest())
+
+
+@dataclass
+class PublicKey:
+    """keypair.rs:29-45: (g1_s, g1_s_x) pairs and g2_s_x for tau, alpha, beta; all uncompressed wire points."""
+    tau_g1: tuple
+    alpha_g1: tuple
+    beta_g1: tuple
+    tau_g2: bytes
+    alpha_g2: bytes
+    beta_g2: bytes
+
+    def serialize(self):
+        """768 bytes, always uncompressed (keypair.rs:105-122)."""
+        return b"".join(bytes(x) for x in (self.tau_g1[0], self.tau_g1[1], self.alpha_g1[0], self.alpha_g1[1],
+                                           self.beta_g1[0], self.beta_g1[1], self.tau_g2, self.alpha_g2, self.beta_g2))
+
+    @classmethod
+    def deserialize(cls, data):
+        """Always checked, no points at infinity (keypair.rs:127-167)."""
+        b = bytes(data)
+        if len(b) < 768:
+            raise DeserializationError("IoError", "public key is 768 bytes")
+        one = (1).to_bytes(32, "big")
+        pts = [b[64 * i: 64 * i + 64] for i in range(6)] + [b[384 + 128 * i: 512 + 128 * i] for i in range(3)]
+        for i, pt in enumerate(pts):
+            try:
+                if _lib.host_mul(int(i >= 6), pt, one)[0] & 0x40:
+                    raise DeserializationError("PointAtInfinity", "in the public key")
+            except _lib.P2BError:
+                raise DeserializationError("DecodingError", "public key element %d" % i)
+        return cls((pts[0], pts[1]), (pts[2], pts[3]), (pts[4], pts[5]), pts[6], pts[7], pts[8])
+
+    def write(self, output_map, accumulator_was_compressed, parameters):
+        """At the end of the response map (keypair.rs:170-191)."""
+        size = parameters.contribution_size if accumulator_was_compressed else parameters.accumulator_size + 768
+        pos = size - parameters.public_key_size if accumulator_was_compressed else parameters.accumulator_size
+        output_map[pos: pos + 768] = np.frombuffer(self.serialize(), dtype=np.uint8)
+
+    @classmethod
+    def read(cls, input_map, accumulator_was_compressed, parameters):
+        """keypair.rs:193-213."""
+        pos = (parameters.contribution_size - parameters.public_key_size if accumulator_was_compressed
+               else parameters.accumulator_size)
+        return cls.deserialize(np.asarray(input_map[pos: pos + 768]).tobytes())
+
+
+def keypair(rng, digest):
+    """keypair(rng, digest) -> (PublicKey, PrivateKey) (keypair.rs:54-103).  `rng` is a lib.ChaChaRng (the reference
+    seeds one from OS entropy + user input, compute_constrained.rs:103-141, or from the beacon hash)."""
+    assert len(digest) == 64
+    tau, alpha, beta = rng.gen_fr(), rng.gen_fr(), rng.gen_fr()
+
+    def op(x, personalization):
+        g1_s = rng.gen_g1()
+        xb = int(x).to_bytes(32, "big")
+        g1_s_x = _lib.host_mul(0, g1_s, xb)
+        g2_s = compute_g2_s(digest, g1_s, g1_s_x, personalization)
+        return (g1_s, g1_s_x), _lib.host_mul(1, g2_s, xb)
+
+    pk_tau, pk_alpha, pk_beta = op(tau, 0), op(alpha, 1), op(beta, 2)
+    return (PublicKey(pk_tau[0], pk_alpha[0], pk_beta[0], pk_tau[1], pk_alpha[1], pk_beta[1]),
+            PrivateKey(tau, alpha, beta))
 
 
 def calculate_hash(input_map):
@@ -165,6 +251,132 @@ class BatchedAccumulator:
             if e.code == _lib.EINFINITY_OUT:
                 raise AssertionError("your contribution happened to produce a point at infinity, please re-run")
             raise
+
+
+def _sections(parameters, compressed):
+    """Byte offset and element size of the five accumulator sections (batched_accumulator.rs:96-178)."""
+    p = parameters
+    g1, g2 = (p.g1_compressed, p.g2_compressed) if compressed else (p.g1, p.g2)
+    out, off = {}, p.hash_size
+    for name, cnt, size, group in (("tau_g1", p.powers_g1_length, g1, 0), ("tau_g2", p.powers_length, g2, 1),
+                                   ("alpha_g1", p.powers_length, g1, 0), ("beta_g1", p.powers_length, g1, 0),
+                                   ("beta_g2", 1, g2, 1)):
+        out[name] = (off, cnt, size, group)
+        off += cnt * size
+    return out
+
+
+def _read_points(ctx, amap, parameters, compressed, checked, name, start, count):
+    """read_chunk for one element type (batched_accumulator.rs:889-1001): `count` points from index `start` as
+    uncompressed wire bytes; decompression and the optional curve check run on the GPU codec; infinity is rejected."""
+    off, total, size, group = _sections(parameters, compressed)[name]
+    count = max(0, min(count, total - start))
+    raw = np.asarray(amap[off + start * size: off + (start + count) * size])
+    try:
+        return ctx.recode(group, raw, _lib.ENC_COMPRESSED if compressed else _lib.ENC_UNCOMPRESSED, _lib.ENC_UNCOMPRESSED,
+                          (_lib.CHECK_INPUT if checked else 0) | _lib.REJECT_INFINITY)
+    except _lib.P2BError as e:
+        BatchedAccumulator._raise(e)
+
+
+def _random_scalars(rng, n):
+    """n scalars below 2^253 < r (the reference draws Fr::rand from thread_rng, utils.rs:118-124)."""
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 0] &= 0x1f
+    return a.reshape(-1)
+
+
+def verify_transformation(input_map, output_map, key, digest, input_is_compressed, output_is_compressed,
+                          check_input_for_correctness, check_output_for_correctness, parameters, ctx=None, rng=None):
+    """BatchedAccumulator::verify_transformation (batched_accumulator.rs:279-540): the proofs of knowledge, the ratio
+    checks on the first elements, then chunk by chunk `same_ratio(power_pairs(after.*), (tau_g2[0], tau_g2[1]))`.
+    power_pairs = two Pippenger MSMs per element type and chunk on the GPU; same_ratio = two pairings on the host.
+    Returns True / False like the reference; a chunk that does not deserialize raises (the reference panics)."""
+    ctx = ctx or BatchedAccumulator.context()
+    rng = rng or np.random.default_rng()
+    assert len(digest) == 64
+    p = parameters
+    tau_g2_s = compute_g2_s(digest, key.tau_g1[0], key.tau_g1[1], 0)
+    alpha_g2_s = compute_g2_s(digest, key.alpha_g1[0], key.alpha_g1[1], 1)
+    beta_g2_s = compute_g2_s(digest, key.beta_g1[0], key.beta_g1[1], 2)
+    # proofs of knowledge: g1^s / g1^(s*x) = g2^s / g2^(s*x)
+    if not same_ratio(key.tau_g1, (tau_g2_s, key.tau_g2)):
+        return False
+    if not same_ratio(key.alpha_g1, (alpha_g2_s, key.alpha_g2)):
+        return False
+    if not same_ratio(key.beta_g1, (beta_g2_s, key.beta_g2)):
+        return False
+
+    def rd(amap, compressed, checked, name, start, count):
+        return _read_points(ctx, amap, p, compressed, checked, name, start, count)
+
+    before = lambda name, start, count: rd(input_map, input_is_compressed, check_input_for_correctness, name, start, count)
+    after = lambda name, start, count: rd(output_map, output_is_compressed, check_output_for_correctness, name, start, count)
+    pt = lambda a, i, size: a[i * size: (i + 1) * size].tobytes()
+
+    b_tau, a_tau = before("tau_g1", 0, 2), after("tau_g1", 0, 2)
+    a_tau2 = after("tau_g2", 0, 2)
+    b_alpha, a_alpha = before("alpha_g1", 0, 2), after("alpha_g1", 0, 2)
+    b_beta, a_beta = before("beta_g1", 0, 2), after("beta_g1", 0, 2)
+    b_beta2, a_beta2 = before("beta_g2", 0, 1), after("beta_g2", 0, 1)
+    if pt(a_tau, 0, 64) != G1_ONE or pt(a_tau2, 0, 128) != G2_ONE:
+        return False
+    if not same_ratio((pt(b_tau, 1, 64), pt(a_tau, 1, 64)), (tau_g2_s, key.tau_g2)):
+        return False
+    if not same_ratio((pt(b_alpha, 0, 64), pt(a_alpha, 0, 64)), (alpha_g2_s, key.alpha_g2)):
+        return False
+    if not same_ratio((pt(b_beta, 0, 64), pt(a_beta, 0, 64)), (beta_g2_s, key.beta_g2)):
+        return False
+    if not same_ratio((pt(b_beta, 0, 64), pt(a_beta, 0, 64)), (pt(b_beta2, 0, 128), pt(a_beta2, 0, 128))):
+        return False
+    g2_pair = (pt(a_tau2, 0, 128), pt(a_tau2, 1, 128))
+    g1_pair = (pt(a_tau, 0, 64), pt(a_tau, 1, 64))
+
+    def powers_ok(group, v, pair):
+        n = v.size // (128 if group else 64)
+        if n < 2:
+            return False                              # merge_pairs of nothing is (0, 0): same_ratio rejects zero
+        s, sx = power_pairs(ctx, group, v, _random_scalars(rng, n - 1))
+        return same_ratio((s, sx), pair) if group == 0 else same_ratio(pair, (s, sx))
+
+    last_first = [None, None]
+    for start in range(0, p.powers_length, p.batch_size):
+        end = min(start + p.batch_size, p.powers_length) - 1
+        if end == start:
+            raise RuntimeError("Chunk does not have a min and max")            # the reference's panic (:462)
+        size = end - start + 1 + (0 if end == p.powers_length - 1 else 1)      # one extra element: chunks overlap
+        if check_input_for_correctness:
+            for name in ("tau_g1", "tau_g2", "alpha_g1", "beta_g1"):
+                before(name, start, size)
+        v = after("tau_g1", start, size)
+        if not powers_ok(0, v, g2_pair):
+            return False
+        if not powers_ok(1, after("tau_g2", start, size), g1_pair):
+            return False
+        if not powers_ok(0, after("alpha_g1", start, size), g2_pair):
+            return False
+        if not powers_ok(0, after("beta_g1", start, size), g2_pair):
+            return False
+        if end == p.powers_length - 1:
+            last_first[0] = pt(v, size - 1, 64)
+    for start in range(p.powers_length, p.powers_g1_length, p.batch_size):
+        end = min(start + p.batch_size, p.powers_g1_length) - 1
+        if end == start:
+            raise RuntimeError("Chunk does not have a min and max")            # (:526)
+        size = end - start + 1 + (0 if end == p.powers_g1_length - 1 else 1)
+        if check_input_for_correctness:
+            before("tau_g1", start, size)
+        v = after("tau_g1", start, size)
+        if not powers_ok(0, v, g2_pair):
+            return False
+        if start == p.powers_length:
+            last_first[1] = pt(v, 0, 64)
+    if last_first[0] is None or last_first[1] is None:
+        return False
+    return powers_ok(0, np.frombuffer(last_first[0] + last_first[1], dtype=np.uint8), g2_pair)
+
+
+BatchedAccumulator.verify_transformation = staticmethod(verify_transformation)
 
 
 def merge_pairs(ctx, group, v1, v2, scalars):
