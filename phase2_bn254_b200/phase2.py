@@ -107,7 +107,7 @@ def merge_pairs(ctx, v1, v2, rng=None):
     if n == 0:
         zero = bytes([0x40]) + bytes(63)
         return zero, zero
-    rho = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    rho = np.frombuffer(bytearray(rng.bytes(32 * n)), dtype=np.uint8).reshape(n, 32)
     rho[:, 0] &= 0x1f                                            # < 2^253 < r
     rho = rho.reshape(-1)
     return ctx.msm(0, v1, rho), ctx.msm(0, v2, rho)

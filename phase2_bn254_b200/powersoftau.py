@@ -281,7 +281,7 @@ def _read_points(ctx, amap, parameters, compressed, checked, name, start, count)
 
 def _random_scalars(rng, n):
     """n scalars below 2^253 < r (the reference draws Fr::rand from thread_rng, utils.rs:118-124)."""
-    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a = np.frombuffer(bytearray(rng.bytes(32 * n)), dtype=np.uint8).reshape(n, 32)
     a[:, 0] &= 0x1f
     return a.reshape(-1)
 
