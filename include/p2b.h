@@ -186,6 +186,17 @@ uint64_t p2b_pot_radix_file_size(uint32_t m);
 int p2b_pot_prepare_phase2(p2b_ctx *ctx, const uint8_t *accumulator, uint64_t accumulator_len, uint32_t size_log2,
                            int compressed_input, int check_input, uint32_t m, uint8_t *out, uint64_t out_len, int flags);
 
+/* ---- sparse linear maps over group elements (the QAP evaluation of MPCParameters::new) ----
+ * out[i] = sum_{j in [row_offsets[i], row_offsets[i+1])} coeffs[j] * bases[cols[j]]   (phase2/src/parameters.rs:225-300:
+ * a_g1, b_g1, b_g2 and ext = ic / l over the Lagrange-basis points of phase1radix2m{m}; rows = variables, entries =
+ * (coefficient, constraint index) pairs of the A / B / C matrices).  CSR layout: row_offsets has n_rows + 1 entries
+ * starting at 0; bases are uncompressed points (decoded checked); coeffs are 32-byte big-endian canonical scalars;
+ * out receives n_rows uncompressed points (empty or cancelling rows give the point at infinity, flag 0x40). */
+int p2b_g1_sparse_mul(p2b_ctx *ctx, const uint8_t *bases, size_t n_bases, const uint64_t *row_offsets,
+                      const uint32_t *cols, const uint8_t *coeffs_be32, size_t n_rows, uint8_t *out);
+int p2b_g2_sparse_mul(p2b_ctx *ctx, const uint8_t *bases, size_t n_bases, const uint64_t *row_offsets,
+                      const uint32_t *cols, const uint8_t *coeffs_be32, size_t n_rows, uint8_t *out);
+
 /* ---- verifier host side: pairings, hash_to_g2, key-generation RNG (CPU code, no ctx, no GPU needed) ----
  * The reference keeps these on the CPU too: a verification does <= 20 pairings (same_ratio,
  * powersoftau/src/utils.rs:151-159, phase2/src/utils.rs:48-57) over pairs that merge_pairs / power_pairs

@@ -135,6 +135,22 @@ def sum_points(group, points):
     return bytes(out)
 
 
+def sparse_mul(group, bases, row_offsets, cols, coeffs):
+    """out[i] = sum_j coeffs[j] * bases[cols[j]] row by row -- the `eval` loop of MPCParameters::new
+    (phase2/src/parameters.rs:244-300: `a_g1.add_assign(&coeffs_g1[lag].mul(coeff))` per (coeff, lag) entry), on the
+    oracle's scalar multiplication and point sum.  Empty rows give the point at infinity."""
+    size = point_size(group, UNCOMPRESSED)
+    out = []
+    for i in range(len(row_offsets) - 1):
+        lo, hi = int(row_offsets[i]), int(row_offsets[i + 1])
+        if lo == hi:
+            out.append(bytes([0x40]) + bytes(size - 1))
+            continue
+        pts = b"".join(bases[size * int(c): size * (int(c) + 1)] for c in cols[lo:hi])
+        out.append(sum_points(group, batch_mul(group, pts, bytes(coeffs[32 * lo: 32 * hi]))))
+    return b"".join(out)
+
+
 def fr_fft(data, inverse=False, coset=False, threads=1):
     n = len(data) // 32
     log_n = n.bit_length() - 1

@@ -28,6 +28,7 @@ SYMBOLS = [
     "p2b_fr_fft", "p2b_fr_fft_dev", "p2b_profile_enable", "p2b_profile_read",
     "p2b_pot_decompress", "p2b_g1_recode", "p2b_g2_recode",
     "p2b_g1_group_fft", "p2b_g2_group_fft", "p2b_pot_radix_file_size", "p2b_pot_prepare_phase2",
+    "p2b_g1_sparse_mul", "p2b_g2_sparse_mul",
     "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
     "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants",
 ]
@@ -94,6 +95,8 @@ def load():
     lib.p2b_pot_radix_file_size.argtypes = [u32]
     lib.p2b_pot_radix_file_size.restype = u64
     lib.p2b_pot_prepare_phase2.argtypes = [vp, u8p, u64, u32, i32, i32, u32, u8p, u64, i32]
+    lib.p2b_g1_sparse_mul.argtypes = [vp, u8p, sz, vp, vp, u8p, sz, u8p]
+    lib.p2b_g2_sparse_mul.argtypes = [vp, u8p, sz, vp, vp, u8p, sz, u8p]
     lib.p2b_pairing_check.argtypes = [u8p, u8p, sz, ctypes.POINTER(i32)]
     lib.p2b_same_ratio.argtypes = [u8p, u8p, u8p, u8p, ctypes.POINTER(i32)]
     lib.p2b_hash_to_g2.argtypes = [u8p, u8p]
@@ -357,6 +360,20 @@ class Context:
         fn = self.lib.p2b_g2_msm if group == G2 else self.lib.p2b_g1_msm
         self._check(fn(self.h, _ptr(pts), _ptr(sc), n, _ptr(out)))
         return out.tobytes()
+
+    def sparse_mul(self, group, bases, row_offsets, cols, coeffs):
+        """out[i] = sum_j coeffs[j] * bases[cols[j]] over CSR rows (the QAP evaluation of MPCParameters::new)."""
+        b, k = _host(bases), _host(coeffs)
+        ro = np.ascontiguousarray(row_offsets, dtype=np.uint64)
+        cl = np.ascontiguousarray(cols, dtype=np.uint32)
+        size = enc_size(group, ENC_UNCOMPRESSED)
+        n_rows = ro.size - 1
+        if n_rows < 0 or k.size != 32 * cl.size or (n_rows >= 0 and int(ro[-1]) != cl.size):
+            raise ValueError("sparse_mul: inconsistent CSR arrays")
+        out = np.empty(max(1, n_rows * size), dtype=np.uint8)
+        fn = self.lib.p2b_g2_sparse_mul if group == G2 else self.lib.p2b_g1_sparse_mul
+        self._check(fn(self.h, _ptr(b), b.size // size, _ptr(ro), _ptr(cl), _ptr(k), n_rows, _ptr(out)))
+        return out[: n_rows * size]
 
     def msm_dev(self, group, d_points, d_scalars, n):
         out = np.empty(enc_size(group, ENC_UNCOMPRESSED), dtype=np.uint8)

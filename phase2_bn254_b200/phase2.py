@@ -39,7 +39,110 @@ def params_layout(buf):
     return lay
 
 
+class SynthesisError(Exception):
+    """bellman SynthesisError (PolynomialDegreeTooLarge, UnconstrainedVariable) as raised by MPCParameters::new."""
+
+
+_R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+class KeypairAssembly:
+    """The constraint system MPCParameters::new synthesizes the circuit into (phase2/src/keypair_assembly.rs:20-118):
+    per variable, the (coefficient, constraint index) entries of the A, B and C matrices.  Variables are ("input", i) /
+    ("aux", i) pairs; a linear combination is a list of (variable, coefficient) with integer coefficients mod r."""
+
+    def __init__(self):
+        self.num_inputs = self.num_aux = self.num_constraints = 0
+        self.at_inputs, self.bt_inputs, self.ct_inputs = [], [], []
+        self.at_aux, self.bt_aux, self.ct_aux = [], [], []
+
+    def alloc(self):
+        index = self.num_aux
+        self.num_aux += 1
+        self.at_aux.append([]); self.bt_aux.append([]); self.ct_aux.append([])
+        return ("aux", index)
+
+    def alloc_input(self):
+        index = self.num_inputs
+        self.num_inputs += 1
+        self.at_inputs.append([]); self.bt_inputs.append([]); self.ct_inputs.append([])
+        return ("input", index)
+
+    def enforce(self, a, b, c):
+        for lc, inputs, aux in ((a, self.at_inputs, self.at_aux), (b, self.bt_inputs, self.bt_aux),
+                                (c, self.ct_inputs, self.ct_aux)):
+            for (kind, index), coeff in lc:
+                (inputs if kind == "input" else aux)[index].append((int(coeff) % _R, self.num_constraints))
+        self.num_constraints += 1
+
+
+def _csr(rows, col_shift=0):
+    offs = np.zeros(len(rows) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in rows], dtype=np.uint64)
+    cols = np.fromiter((lag + col_shift for r in rows for _, lag in r), dtype=np.uint32, count=int(offs[-1]))
+    coeffs = b"".join(int(cf).to_bytes(32, "big") for r in rows for cf, _ in r)
+    return offs, cols, np.frombuffer(coeffs, dtype=np.uint8)
+
+
 class MPCParameters:
+    @classmethod
+    def new(cls, circuit, should_filter_points_at_infinity, radix, ctx=None):
+        """MPCParameters::new (phase2/src/parameters.rs:98-386).  `circuit(cs)` synthesizes into a KeypairAssembly (the
+        ONE input is allocated first, the x * 0 = 0 input constraints are appended, exactly as the reference does);
+        `radix(exp)` returns the bytes of phase1radix2m{exp} (prepare_phase2's output).  The QAP evaluation -- one scalar
+        multiplication per matrix entry, summed per variable -- runs on the GPU (p2b_g{1,2}_sparse_mul)."""
+        ctx = ctx or _lib.Context(0)
+        cs = KeypairAssembly()
+        cs.alloc_input()
+        circuit(cs)
+        for i in range(cs.num_inputs):
+            cs.enforce([(("input", i), 1)], [], [])
+        m, exp = 1, 0
+        while m < cs.num_constraints:
+            m, exp = m * 2, exp + 1
+            if exp > 28:
+                raise SynthesisError("PolynomialDegreeTooLarge")
+        f = np.frombuffer(bytes(radix(exp)), dtype=np.uint8)
+        if f.size < 192 + 384 * m:
+            raise IOError("UnexpectedEof: phase1radix2m%d is too short" % exp)
+        sizes = (("alpha", 64, 1), ("beta_g1", 64, 1), ("beta_g2", 128, 1), ("coeffs_g1", 64, m), ("coeffs_g2", 128, m),
+                 ("alpha_coeffs_g1", 64, m), ("beta_coeffs_g1", 64, m), ("h", 64, m - 1))
+        sec, off = {}, 0
+        for name, size, cnt in sizes:
+            sec[name] = f[off: off + size * cnt]
+            if cnt and (sec[name].reshape(cnt, size)[:, 0] & 0x40).any():
+                raise IOError("InvalidData: point at infinity")                      # read_g1 / read_g2 (:156-180)
+            off += size * cnt
+        at, bt, ct = cs.at_inputs + cs.at_aux, cs.bt_inputs + cs.bt_aux, cs.ct_inputs + cs.ct_aux
+        a_off, a_cols, a_k = _csr(at)
+        b_off, b_cols, b_k = _csr(bt)
+        a_g1 = ctx.sparse_mul(0, sec["coeffs_g1"], a_off, a_cols, a_k)
+        b_g1 = ctx.sparse_mul(0, sec["coeffs_g1"], b_off, b_cols, b_k)
+        b_g2 = ctx.sparse_mul(1, sec["coeffs_g2"], b_off, b_cols, b_k)
+        # ext = A . beta_coeffs + B . alpha_coeffs + C . coeffs  (:285-297): one product over the three bases side by side
+        ext_rows = [[(cf, lag) for cf, lag in ra] + [(cf, lag + m) for cf, lag in rb] + [(cf, lag + 2 * m) for cf, lag in rc]
+                    for ra, rb, rc in zip(at, bt, ct)]
+        e_off, e_cols, e_k = _csr(ext_rows)
+        ext = ctx.sparse_mul(0, np.concatenate([sec["beta_coeffs_g1"], sec["alpha_coeffs_g1"], sec["coeffs_g1"]]),
+                             e_off, e_cols, e_k)
+        ic, l = ext[: 64 * cs.num_inputs], ext[64 * cs.num_inputs:]
+        if l.size and (l.reshape(-1, 64)[:, 0] & 0x40).any():
+            raise SynthesisError("UnconstrainedVariable")
+
+        def vec(points, size, filt):
+            p = points.reshape(-1, size)
+            if filt:
+                p = p[(p[:, 0] & 0x40) == 0]
+            return struct.pack(">I", p.shape[0]) + p.tobytes()
+
+        from .powersoftau import G1_ONE, G2_ONE
+        flt = bool(should_filter_points_at_infinity)
+        body = (sec["alpha"].tobytes() + sec["beta_g1"].tobytes() + sec["beta_g2"].tobytes() + G2_ONE + G1_ONE + G2_ONE +
+                vec(ic, 64, False) + vec(sec["h"], 64, False) + vec(l, 64, False) + vec(a_g1, 64, flt) +
+                vec(b_g1, 64, flt) + vec(b_g2, 128, flt))
+        cs_hash = hashlib.blake2b(body).digest()                                     # HashWriter over params.write (:365-375)
+        return cls(body + cs_hash + struct.pack(">I", 0))
+
     def __init__(self, data):
         self.data = np.array(np.frombuffer(bytes(data), dtype=np.uint8)) if not isinstance(data, np.ndarray) else data
 
