@@ -438,14 +438,37 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
         pin.copy_(torch.frombuffer(params, dtype=torch.uint8))
         pout = torch.empty(len(params) + 384, dtype=torch.uint8, pin_memory=True)
         times = []
+        s_g1 = np.frombuffer(g1(5), dtype=np.uint8)
+        r_g2 = np.frombuffer(lib.hash_to_g2(ctx.phase2_transcript(pin.numpy(), k, s_g1)), dtype=np.uint8)   # keypair(): r = hash_to_g2(transcript)
         for _ in range(3):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            _, h = ctx.phase2_contribute(pin.numpy(), k, np.frombuffer(g1(5), dtype=np.uint8), np.frombuffer(g2, dtype=np.uint8),
-                                         out=pout.numpy())
+            _, h = ctx.phase2_contribute(pin.numpy(), k, s_g1, r_g2, out=pout.numpy())
             times.append(time.perf_counter() - t0)
         out["phase2_contribute_2^20"] = {"wall_s": round(min(times), 4), "points": nh + nl, "params_bytes": len(params),
                                          "contribution_hash": h.hex()[:32]}
+        # -- next row: verify_contribution of that contribution: merge_pairs over H and L = four 2^20-term
+        #    MSMs on the GPU, same_ratio pairings on the host
+        from phase2_bn254_b200.phase2 import MPCParameters, verify_contribution
+        t0 = time.perf_counter()
+        vh = verify_contribution(MPCParameters(pin.numpy()), MPCParameters(pout.numpy()), ctx=ctx, rng=np.random.default_rng(7))
+        out["phase2_verify_contribution_2^20"] = {"wall_s": round(time.perf_counter() - t0, 4), "accepted": bool(vh == h)}
+        # -- next row: the QAP evaluation of MPCParameters::new as a sparse group linear map: 2^20 variables
+        #    (rows) with 3 random (coefficient, constraint) entries each over 2^20 Lagrange-basis points
+        nv = 1 << 20
+        rs = np.random.default_rng(11)
+        offs = np.arange(0, 3 * nv + 1, 3, dtype=np.uint64)
+        cols = rs.integers(0, nv, size=3 * nv, dtype=np.uint32)
+        cf = np.frombuffer(bytearray(rs.bytes(96 * nv)), dtype=np.uint8).reshape(-1, 32)
+        cf[:, 0] &= 0x1f
+        bases = np.frombuffer(hl[: nv * 64], dtype=np.uint8)
+        ctx.sparse_mul(0, bases, offs[:1025], cols[:3072], cf[:3072].reshape(-1))
+        t0 = time.perf_counter()
+        sp = ctx.sparse_mul(0, bases, offs, cols, cf.reshape(-1))
+        dt = time.perf_counter() - t0
+        import hashlib as _hl
+        out["mpc_new_sparse_mul_2^20"] = {"wall_s": round(dt, 4), "rows": nv, "entries": 3 * nv, "Mentries_per_s": round(3 * nv / dt / 1e6, 2),
+                                          "out_blake2b": _hl.blake2b(sp.tobytes()).hexdigest()[:32]}
     # -- configs 1 / phase-1 hot path: BatchedAccumulator::transform on the deterministic initial challenge (all generators,
     #    new_constrained), host maps in / out, compressed response; Blake2b-512 of the response body = "response hash"
     import hashlib

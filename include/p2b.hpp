@@ -201,7 +201,51 @@ class MPCParameters {
     }
 };
 
+
+// eval() of MPCParameters::new (parameters.rs:244-300) as one sparse linear map over group elements: CSR rows = variables,
+// (coeff, lag) entries of the A / B / C matrices; out[i] = sum_j coeffs[j] * bases[cols[j]] (uncompressed, infinity allowed).
+inline std::vector<uint8_t> sparse_eval_g1(const Context &ctx, const uint8_t *bases, size_t n_bases, const std::vector<uint64_t> &row_offsets,
+                                           const std::vector<uint32_t> &cols, const std::vector<Scalar> &coeffs) {
+    if (row_offsets.empty() || cols.size() != coeffs.size() || row_offsets.back() != cols.size()) throw std::invalid_argument("sparse_eval: inconsistent CSR arrays");
+    std::vector<uint8_t> out((row_offsets.size() - 1) * 64), k(coeffs.size() * 32);
+    for (size_t i = 0; i < coeffs.size(); i++) memcpy(&k[32 * i], coeffs[i].data(), 32);
+    ctx.check(p2b_g1_sparse_mul(ctx.get(), bases, n_bases, row_offsets.data(), cols.data(), k.data(), row_offsets.size() - 1, out.data()));
+    return out;
+}
+inline std::vector<uint8_t> sparse_eval_g2(const Context &ctx, const uint8_t *bases, size_t n_bases, const std::vector<uint64_t> &row_offsets,
+                                           const std::vector<uint32_t> &cols, const std::vector<Scalar> &coeffs) {
+    if (row_offsets.empty() || cols.size() != coeffs.size() || row_offsets.back() != cols.size()) throw std::invalid_argument("sparse_eval: inconsistent CSR arrays");
+    std::vector<uint8_t> out((row_offsets.size() - 1) * 128), k(coeffs.size() * 32);
+    for (size_t i = 0; i < coeffs.size(); i++) memcpy(&k[32 * i], coeffs[i].data(), 32);
+    ctx.check(p2b_g2_sparse_mul(ctx.get(), bases, n_bases, row_offsets.data(), cols.data(), k.data(), row_offsets.size() - 1, out.data()));
+    return out;
+}
+
 }  // namespace phase2
+
+// ---- host side of the verifiers and of key generation (CPU code in libp2b.so, no Context needed) ----
+// same_ratio (powersoftau/src/utils.rs:151-159, phase2/src/utils.rs:48-57): e(g1.0, g2.1) == e(g1.1, g2.0); false if any point is zero.
+inline bool same_ratio(const uint8_t g1_0[64], const uint8_t g1_1[64], const uint8_t g2_0[128], const uint8_t g2_1[128]) {
+    int same = 0;
+    if (p2b_same_ratio(g1_0, g1_1, g2_0, g2_1, &same) != P2B_OK) throw std::invalid_argument("same_ratio: a point does not decode");
+    return same != 0;
+}
+// hash_to_g2 (utils.rs:31-45): uncompressed G2 point from the first 32 bytes of `digest`.
+inline std::array<uint8_t, 128> hash_to_g2(const uint8_t *digest) {
+    std::array<uint8_t, 128> out;
+    if (p2b_hash_to_g2(digest, out.data()) != P2B_OK) throw std::invalid_argument("hash_to_g2");
+    return out;
+}
+// rand 0.4.6 ChaChaRng::from_seed(&[u32; 8]) with the samplers keypair() uses (keypair.rs:54-103, parameters.rs:860-908).
+class ChaChaRng {
+    uint8_t st_[P2B_RNG_STATE_BYTES];
+   public:
+    explicit ChaChaRng(const uint32_t seed[8]) { p2b_rng_seed(st_, seed); }
+    uint32_t next_u32() { uint32_t v = 0; p2b_rng_u32(st_, &v); return v; }
+    Scalar gen_fr() { Scalar k; p2b_rng_fr(st_, k.data()); return k; }
+    std::array<uint8_t, 64> gen_g1() { std::array<uint8_t, 64> p; p2b_rng_g1(st_, p.data()); return p; }
+    std::array<uint8_t, 128> gen_g2() { std::array<uint8_t, 128> p; p2b_rng_g2(st_, p.data()); return p; }
+};
 
 namespace bellman {
 

@@ -12,9 +12,9 @@
 //       V     = DFT_R(v)                                                           (r DIF stages in smem)
 //       out[(j div Ns) * Ns * R + (j mod Ns) + q * Ns] = V[q]                      (autosort scatter)
 // A block owns a tile of J = 2048 / R consecutive columns so that every global access is a run of J (first
-// pass: R) consecutive 32-byte elements.  The first pass decodes the wire form (big-endian canonical -> Montgomery),
-// the last pass encodes it again and folds in the 1/n of the inverse transform, so the data makes exactly
-// `passes` round trips through HBM.  Algorithmic traffic: 64 B per element; actual: 64 B x passes.
+// pass: R) consecutive 32-byte elements.  The first pass decodes the wire form (big-endian words; no Montgomery conversion
+// is needed, see the load step), the last pass encodes it again and applies the 1/n of the inverse transform, so the data
+// makes exactly `passes` round trips through HBM.  Algorithmic traffic: 64 B per element; actual: 64 B x passes.
 // Twiddles: w^e for e < n comes from a two-level table (2^ceil(log n / 2) + 2^floor(log n / 2) entries, L2
 // resident); the in-tile twiddles omega_256^t sit in shared memory.
 #include <cstdio>
@@ -34,7 +34,8 @@ struct FftPass {
     uint32_t log_n, r, log_ns, log_te;    // tile has 2^log_te elements = 2^(log_te - r) columns x 2^r
     uint32_t lb;                          // bits of the low twiddle table
     const Fr *tlo, *thi, *twr;
-    uint32_t scale[8];                    // LAST: raw multiplier (1 or n^-1, canonical limbs)
+    uint32_t scale[8];                    // LAST, inverse transform: n^-1 in Montgomery form
+    uint32_t do_scale;
     unsigned long long *err;
 };
 
@@ -60,7 +61,9 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK) k_
             uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             v = limbs_from_be_words<FrP>(w);
             if (!is_canonical(v)) atomicMin(p.err, (unsigned long long)(((uint64_t)idx << 8) | (P2B_EARG << 4)));
-            v = to_mont(v);
+            // No conversion to Montgomery form: the canonical words are read AS a Montgomery representation, i.e. of the value
+            // a / R.  The transform is linear and every twiddle is a true Montgomery constant, so the words after the last
+            // pass represent DFT(a) / R -- which are the canonical words of DFT(a).  Saves two multiplications per element.
         } else {
             v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
             if (p.log_ns) {
@@ -115,7 +118,7 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK) k_
         const size_t idx = (((j >> p.log_ns) << (p.log_ns + r)) | k) + ((size_t)q << p.log_ns);
         uint32_t o[8];
         if (LAST) {
-            v = mul(v, scale);                                        // Montgomery -> canonical (x n^-1)
+            if (p.do_scale) v = mul(v, scale);                        // inverse transform: x n^-1 (Montgomery constant)
             limbs_to_be_words(v, o);
         } else {
 #pragma unroll
@@ -258,10 +261,10 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
     FftPass p;
     memset(&p, 0, sizeof p);
     p.log_n = log_n; p.log_te = pl.log_te; p.lb = lb; p.tlo = tlo; p.thi = thi; p.twr = twr; p.err = c->d_err;
-    Fr scale = fp_zero<FrP>();
-    scale.l[0] = 1;
-    if (inverse) scale = from_mont(inv(host_fr_from_u64((uint64_t)n)));    // canonical n^-1 (domain.rs:163-173)
+    Fr scale = fp_one<FrP>();
+    if (inverse) scale = inv(host_fr_from_u64((uint64_t)n));               // n^-1 (domain.rs:163-173)
     memcpy(p.scale, scale.l, 32);
+    p.do_scale = inverse ? 1u : 0u;
     const uint32_t te = 1u << pl.log_te;
     const size_t smem = (size_t)(8 * (te + (te >> 5) + 1) + 8 * 128) * 4;
     const uint32_t blocks = (uint32_t)(n >> pl.log_te);

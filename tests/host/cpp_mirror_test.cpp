@@ -63,6 +63,29 @@ int main(int argc, char **argv) {
         spit(dir + "/fft", dom.coeffs.data(), dom.coeffs.size());
         dom.ifft(ctx);
         spit(dir + "/fft_roundtrip", dom.coeffs.data(), dom.coeffs.size());
+        // verifier host side: tau_g1[0..2] of the new challenge is (G, tau G) and tau_g2[0..2] is (H, tau H): same ratio, and not
+        // the other way round (test_same_ratio_bn256, powersoftau/src/utils.rs:76-88)
+        {
+            const uint8_t *tg1 = next.data() + 64, *tg2 = next.data() + 64 + params.powers_g1_length * 64;
+            if (!p2b::same_ratio(tg1, tg1 + 64, tg2, tg2 + 128) || p2b::same_ratio(tg1 + 64, tg1, tg2, tg2 + 128)) {
+                std::cerr << "same_ratio mismatch\n";
+                return 1;
+            }
+            // QAP-style sparse evaluation over tau_g1: row 0 = 1*P0 + 1*P1, row 1 empty, row 2 = s0*P2
+            std::vector<uint64_t> ro = {0, 2, 2, 3};
+            std::vector<uint32_t> cols = {0, 1, 2};
+            Scalar one{};
+            one[31] = 1;
+            std::vector<Scalar> cf = {one, one, coeffs[0]};
+            auto ev = phase2::sparse_eval_g1(ctx, tg1, params.powers_g1_length, ro, cols, cf);
+            spit(dir + "/sparse", ev.data(), ev.size());
+            // the key-generation RNG is deterministic in its seed
+            const uint32_t seed[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+            p2b::ChaChaRng r1(seed), r2(seed);
+            if (r1.gen_fr() != r2.gen_fr() || r1.gen_g1() != r2.gen_g1() || r1.gen_g2() != r2.gen_g2()) return 1;
+            auto hg = p2b::hash_to_g2(response.data());
+            spit(dir + "/hash_to_g2", hg.data(), hg.size());
+        }
         // error behaviour: a point at infinity in the input is DeserializationError::PointAtInfinity
         challenge[64] = 0x40;
         memset(challenge.data() + 65, 0, 63);

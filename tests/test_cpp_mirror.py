@@ -52,3 +52,8 @@ def test_cpp_mirror_matches_oracle(exe, tmp_path, oracle):
     c = lib.Context(0)
     assert rd("phase1radix2m") == c.pot_prepare_phase2(np.frombuffer(exp, dtype=np.uint8), size, size, True, True).tobytes()
     c.close()
+    # sparse evaluation over tau_g1 (rows: P0 + P1, empty, s0 * P2) and hash_to_g2 of the response's first 32 bytes
+    tg1 = nxt[64:]
+    assert rd("sparse") == (oracle.sum_points(0, tg1[:128]) + bytes([0x40]) + bytes(63) +
+                            oracle.point_mul(0, tg1[128:192], sc[:32]))
+    assert rd("hash_to_g2") == lib.hash_to_g2(rd("response")[:32])

@@ -27,3 +27,13 @@ for chunk in [int(a) for a in sys.argv[2:]] or [22, 23, 24, 25]:
         ts.append((time.perf_counter() - t0) * 1e3)
     assert r == ref
     print("max chunk 2^%d: %s ms" % (chunk, " ".join("%.1f" % t for t in ts)), flush=True)
+# where does the streamed path spend its time?  CUDA-event brackets of the library around the sort / accumulate / reduce kernels
+os.environ["P2B_MSM_STREAM_CHUNK"] = str(1 << 24)
+for label, fn in (("device-resident", lambda: ctx.msm_dev(0, pts.data_ptr(), sc.data_ptr(), n)), ("streamed from the host", lambda: ctx.msm(0, hp.numpy(), hs.numpy()))):
+    ctx.profile(True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    fn()
+    wall = (time.perf_counter() - t0) * 1e3
+    prof = {name: ctx.profile_read(slot) for name, slot in (("sort", lib.PROF_MSM_SORT), ("accumulate", lib.PROF_MSM_ACCUMULATE), ("reduce", lib.PROF_MSM_REDUCE))}
+    ctx.profile(False)
+    print("%s: wall %.1f ms; " % (label, wall) + "; ".join("%s %.1f ms in %d kernels" % (k, v[0], v[1]) for k, v in prof.items()), flush=True)
