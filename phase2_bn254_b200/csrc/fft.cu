@@ -41,7 +41,7 @@ struct FftPass {
 
 __device__ __forceinline__ uint32_t fft_phys(uint32_t slot) { return slot + (slot >> 5); }
 
-template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK) k_fft_pass(FftPass p) {
+template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, 2) k_fft_pass(FftPass p) {
     extern __shared__ __align__(16) uint32_t sm[];
     const uint32_t te = 1u << p.log_te, plane = te + (te >> 5) + 1;
     uint32_t *u = sm;                      // 8 planes of `plane` words
@@ -79,7 +79,11 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK) k_
     }
     __syncthreads();
     // ---- r decimation-in-frequency stages: u[bitrev(q)] = V[q] ----
-    for (uint32_t s = 0; s < r; s++) {
+    // The last three stages (butterfly spans 4, 2, 1) run in registers, one radix-8 group per thread: their twiddles are
+    // omega_8^p only, and the trivial ones (p = 0) are known at compile time: 5 multiplications per 8 elements instead of 8,
+    // and two shared-memory round trips less.
+    const uint32_t smem_stages = r >= 3 ? r - 3 : r;
+    for (uint32_t s = 0; s < smem_stages; s++) {
         const uint32_t lh = r - 1 - s, half = 1u << lh;
         for (uint32_t bi = tid; bi < (te >> 1); bi += FFT_BLOCK) {
             const uint32_t jj = bi & (J - 1), b = bi >> log_j;
@@ -98,6 +102,51 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK) k_
             }
 #pragma unroll
             for (int w = 0; w < 8; w++) { u[w * plane + p0] = sum.l[w]; u[w * plane + p1] = d.l[w]; }
+        }
+        __syncthreads();
+    }
+    if (r >= 3) {
+        Fr w8[3];                                                      // omega_8^1, ^2, ^3 = omega_256^32, ^64, ^96
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int w = 0; w < 8; w++) w8[k].l[w] = tw[w * 128 + 32 * (k + 1)];
+        const uint32_t log_g = r - 3;                                  // radix-8 groups per column
+        for (uint32_t gi = tid; gi < (te >> 3); gi += FFT_BLOCK) {
+            const uint32_t g = gi & ((1u << log_g) - 1u), jj = gi >> log_g;
+            Fr x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t ph = fft_phys((g * 8 + k) * J + jj);
+#pragma unroll
+                for (int w = 0; w < 8; w++) x[k].l[w] = u[w * plane + ph];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {                              // span 4: twiddle omega_8^q
+                Fr sum = add(x[q], x[q + 4]), d = sub(x[q], x[q + 4]);
+                x[q] = sum;
+                x[q + 4] = q ? mul(d, w8[q - 1]) : d;
+            }
+#pragma unroll
+            for (int base = 0; base < 8; base += 4)
+#pragma unroll
+                for (int q = 0; q < 2; q++) {                          // span 2: twiddle omega_4^q
+                    Fr sum = add(x[base + q], x[base + q + 2]), d = sub(x[base + q], x[base + q + 2]);
+                    x[base + q] = sum;
+                    x[base + q + 2] = q ? mul(d, w8[1]) : d;
+                }
+#pragma unroll
+            for (int base = 0; base < 8; base += 2) {                  // span 1: no twiddle
+                Fr sum = add(x[base], x[base + 1]), d = sub(x[base], x[base + 1]);
+                x[base] = sum;
+                x[base + 1] = d;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t ph = fft_phys((g * 8 + k) * J + jj);
+#pragma unroll
+                for (int w = 0; w < 8; w++) u[w * plane + ph] = x[k].l[w];
+            }
         }
         __syncthreads();
     }
