@@ -27,6 +27,12 @@ namespace p2b {
 static constexpr int FFT_BLOCK = 256;
 static constexpr int FFT_TILE_LOG = 11;   // elements per tile (64 KB of shared memory + padding)
 static constexpr int FFT_RMAX = 8;        // stages per pass
+#ifndef FFT_REG_STAGES
+#define FFT_REG_STAGES 3                  // last stages of a pass done in registers (3: radix-8 groups, 2: radix-4)
+#endif
+#ifndef FFT_MIN_BLOCKS
+#define FFT_MIN_BLOCKS 3
+#endif
 
 struct FftPass {
     const uint32_t *in;
@@ -41,7 +47,7 @@ struct FftPass {
 
 __device__ __forceinline__ uint32_t fft_phys(uint32_t slot) { return slot + (slot >> 5); }
 
-template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, 2) k_fft_pass(FftPass p) {
+template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, FFT_MIN_BLOCKS) k_fft_pass(FftPass p) {
     extern __shared__ __align__(16) uint32_t sm[];
     const uint32_t te = 1u << p.log_te, plane = te + (te >> 5) + 1;
     uint32_t *u = sm;                      // 8 planes of `plane` words
@@ -79,10 +85,10 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, 2)
     }
     __syncthreads();
     // ---- r decimation-in-frequency stages: u[bitrev(q)] = V[q] ----
-    // The last three stages (butterfly spans 4, 2, 1) run in registers, one radix-8 group per thread: their twiddles are
-    // omega_8^p only, and the trivial ones (p = 0) are known at compile time: 5 multiplications per 8 elements instead of 8,
-    // and two shared-memory round trips less.
-    const uint32_t smem_stages = r >= 3 ? r - 3 : r;
+    // The last FFT_REG_STAGES stages (butterfly spans 4, 2, 1) run in registers, one radix-8 (radix-4) group per thread: their
+    // twiddles are omega_8^p only, and the trivial ones (p = 0) are known at compile time: 5 multiplications per 8 elements
+    // instead of 8 (1 per 4 instead of 2), and two (one) shared-memory round trips less.
+    const uint32_t smem_stages = r >= FFT_REG_STAGES ? r - FFT_REG_STAGES : r;
     for (uint32_t s = 0; s < smem_stages; s++) {
         const uint32_t lh = r - 1 - s, half = 1u << lh;
         for (uint32_t bi = tid; bi < (te >> 1); bi += FFT_BLOCK) {
@@ -105,30 +111,33 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, 2)
         }
         __syncthreads();
     }
-    if (r >= 3) {
+    if (r >= FFT_REG_STAGES) {
+        constexpr int RG = 1 << FFT_REG_STAGES;                        // 8 (or 4) elements per thread
         Fr w8[3];                                                      // omega_8^1, ^2, ^3 = omega_256^32, ^64, ^96
 #pragma unroll
         for (int k = 0; k < 3; k++)
 #pragma unroll
             for (int w = 0; w < 8; w++) w8[k].l[w] = tw[w * 128 + 32 * (k + 1)];
-        const uint32_t log_g = r - 3;                                  // radix-8 groups per column
-        for (uint32_t gi = tid; gi < (te >> 3); gi += FFT_BLOCK) {
+        const uint32_t log_g = r - FFT_REG_STAGES;                     // register groups per column
+        for (uint32_t gi = tid; gi < (te >> FFT_REG_STAGES); gi += FFT_BLOCK) {
             const uint32_t g = gi & ((1u << log_g) - 1u), jj = gi >> log_g;
-            Fr x[8];
+            Fr x[RG];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t ph = fft_phys((g * 8 + k) * J + jj);
+            for (int k = 0; k < RG; k++) {
+                const uint32_t ph = fft_phys((g * RG + k) * J + jj);
 #pragma unroll
                 for (int w = 0; w < 8; w++) x[k].l[w] = u[w * plane + ph];
             }
+            if (RG == 8) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {                              // span 4: twiddle omega_8^q
-                Fr sum = add(x[q], x[q + 4]), d = sub(x[q], x[q + 4]);
-                x[q] = sum;
-                x[q + 4] = q ? mul(d, w8[q - 1]) : d;
+                for (int q = 0; q < 4; q++) {                          // span 4: twiddle omega_8^q
+                    Fr sum = add(x[q], x[q + 4]), d = sub(x[q], x[q + 4]);
+                    x[q] = sum;
+                    x[q + 4] = q ? mul(d, w8[q - 1]) : d;
+                }
             }
 #pragma unroll
-            for (int base = 0; base < 8; base += 4)
+            for (int base = 0; base < RG; base += 4)
 #pragma unroll
                 for (int q = 0; q < 2; q++) {                          // span 2: twiddle omega_4^q
                     Fr sum = add(x[base + q], x[base + q + 2]), d = sub(x[base + q], x[base + q + 2]);
@@ -136,14 +145,14 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, 2)
                     x[base + q + 2] = q ? mul(d, w8[1]) : d;
                 }
 #pragma unroll
-            for (int base = 0; base < 8; base += 2) {                  // span 1: no twiddle
+            for (int base = 0; base < RG; base += 2) {                 // span 1: no twiddle
                 Fr sum = add(x[base], x[base + 1]), d = sub(x[base], x[base + 1]);
                 x[base] = sum;
                 x[base + 1] = d;
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t ph = fft_phys((g * 8 + k) * J + jj);
+            for (int k = 0; k < RG; k++) {
+                const uint32_t ph = fft_phys((g * RG + k) * J + jj);
 #pragma unroll
                 for (int w = 0; w < 8; w++) u[w * plane + ph] = x[k].l[w];
             }
