@@ -500,6 +500,17 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
         if size == 10:
             out["_pot10"] = (chn.tobytes(), key, rsn[64:end].tobytes())
         if size == 20:
+            # -- next row: verify_transformation of that response (compressed) against the challenge: per chunk
+            #    of 2^18 powers eight Pippenger MSMs on the GPU (power_pairs over tau_g1, tau_g2, alpha_g1, beta_g1), the
+            #    same_ratio pairings on host threads
+            from phase2_bn254_b200.powersoftau import public_key_for, verify_transformation
+            digest = hashlib.blake2b(b"bench digest").digest()
+            pub = public_key_for(key, lib.ChaChaRng([7] * 8), digest)
+            t0 = time.perf_counter()
+            ok = verify_transformation(chn, rsn, pub, digest, False, True, False, False, CeremonyParams(size, 1 << 18), ctx=ctx,
+                                       rng=np.random.default_rng(3))
+            out["pot_verify_transformation_2^20"] = {"wall_s": round(time.perf_counter() - t0, 4), "accepted": bool(ok),
+                                                     "chunk": 1 << 18}
             # -- next row: prepare_phase2 for m = 16 from that compressed response: 3 G1 + 1 G2 group iFFTs
             #    of 2^16 points (d/2 log d scalar multiplications each) + the H query
             from phase2_bn254_b200.powersoftau import prepare_phase2

@@ -199,6 +199,11 @@ static __global__ void k_fft_tables(Fr *tlo, Fr *thi, Fr *twr, Fr base, Fr root2
     } else if (twr && i < nlo + nhi + 128) twr[i - nlo - nhi] = pow_u64(root256, i - nlo - nhi);
 }
 
+static __global__ void k_fft_scale_table(Fr *dst, const Fr *src, uint32_t n, Fr k) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = mul(src[i], k);
+}
+
 // data[i] <- data[i] * g^i on the wire form (distribute_powers, domain.rs:176-189)
 static __global__ void __launch_bounds__(256) k_fr_distribute_powers(uint32_t *data, size_t n, const Fr *glo, const Fr *ghi_raw,
                                                                       uint32_t lb, unsigned long long *err) {
@@ -267,7 +272,7 @@ static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
     if (c->fft_tw.p && c->fft_tw_log_n == log_n && c->fft_tw_inverse == inverse) return P2B_OK;
     const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
     const size_t nent = ((size_t)1 << lb) + ((size_t)1 << hb) + 128;
-    int rc = dev_reserve(c, c->fft_tw, 2 * nent * sizeof(Fr));      // [omega tables | coset tables]
+    int rc = dev_reserve(c, c->fft_tw, (2 * nent + ((size_t)1 << hb)) * sizeof(Fr));      // [omega tables | coset tables | thi x n^-1]
     if (rc) return rc;
     Fr root = host_root_of_unity(), omega = root, root256 = root;
     for (uint32_t i = log_n; i < 28; i++) omega = sqr(omega);
@@ -279,7 +284,10 @@ static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
     const uint32_t threads = (uint32_t)nent;
     k_fft_tables<<<(threads + 127) / 128, 128, 0, c->stream>>>(tlo, thi, twr, omega, root256, lb, hb, 0);
     k_fft_tables<<<(threads + 127) / 128, 128, 0, c->stream>>>(glo, ghi, nullptr, g, g, lb, hb, 1);
-    c->launches += 2;
+    // inverse transform: the 1/n is folded into the high twiddle table the LAST pass uses (no separate multiplication)
+    Fr ninv = inverse ? inv(host_fr_from_u64((uint64_t)1 << log_n)) : fp_one<FrP>();
+    k_fft_scale_table<<<(int)((((size_t)1 << hb) + 127) / 128), 128, 0, c->stream>>>((Fr *)c->fft_tw.p + 2 * nent, thi, (uint32_t)1 << hb, ninv);
+    c->launches += 3;
     P2B_CUDA(c, cudaGetLastError());
     c->fft_tw_log_n = log_n;
     c->fft_tw_inverse = inverse;
@@ -301,7 +309,8 @@ template <bool FIRST, bool LAST> static int fft_launch_pass(Ctx *c, const FftPas
 }
 
 // d_data: 2^log_n wire scalars; d_tmp: scratch of the same size.  The result lands in *d_result (d_data or d_tmp).
-static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int inverse, int coset, void **d_result) {
+// With a second scratch buffer a three-pass transform runs data -> tmp -> tmp2 -> data and needs no copy back.
+static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int inverse, int coset, void **d_result, void *d_tmp2 = nullptr) {
     if (log_n > 28) return ctx_fail(c, P2B_EARG, "fft: log_n must be <= 28 (Fr::S, domain.rs:64-78)");
     int rc = fft_tables(c, log_n, inverse);
     if (rc) return rc;
@@ -309,6 +318,7 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
     const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
     Fr *tlo = (Fr *)c->fft_tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
     Fr *glo = twr + 128, *ghi = glo + ((size_t)1 << lb);
+    const Fr *thi_scaled = (const Fr *)c->fft_tw.p + 2 * (((size_t)1 << lb) + ((size_t)1 << hb) + 128);
     int sgrid = (int)((n + 255) / 256);
     if (sgrid > c->sm_count * 8) sgrid = c->sm_count * 8;
     if (coset && !inverse) {   // coset_fft: distribute_powers(g) then fft (domain.rs:191-195)
@@ -327,17 +337,23 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
     const size_t smem = (size_t)(8 * (te + (te >> 5) + 1) + 8 * 128) * 4;
     const uint32_t blocks = (uint32_t)(n >> pl.log_te);
     void *src = d_data, *dst = d_tmp;
+    const bool via_tmp2 = d_tmp2 && pl.npass == 3;
     uint32_t log_ns = 0;
     for (uint32_t i = 0; i < pl.npass; i++) {
+        if (via_tmp2) dst = i == 0 ? d_tmp : i == 1 ? d_tmp2 : d_data;
         p.in = (const uint32_t *)src; p.out = (uint32_t *)dst; p.r = pl.r[i]; p.log_ns = log_ns;
         const bool first = i == 0, last = i + 1 == pl.npass;
+        if (last && inverse && !first) {                               // the twiddle at load already carries 1/n
+            p.thi = thi_scaled;
+            p.do_scale = 0;
+        }
         if (first && last) rc = fft_launch_pass<true, true>(c, p, blocks, smem);
         else if (first) rc = fft_launch_pass<true, false>(c, p, blocks, smem);
         else if (last) rc = fft_launch_pass<false, true>(c, p, blocks, smem);
         else rc = fft_launch_pass<false, false>(c, p, blocks, smem);
         if (rc) return rc;
         log_ns += pl.r[i];
-        void *t = src; src = dst; dst = t;
+        void *t = src; src = dst; dst = t;                             // (dst is overridden above when via_tmp2)
     }
     if (coset && inverse) {    // icoset_fft: ifft then distribute_powers(g^-1) (domain.rs:197-205)
         k_fr_distribute_powers<<<sgrid, 256, 0, c->stream>>>((uint32_t *)src, n, glo, ghi, lb, c->d_err);
@@ -350,10 +366,11 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
 
 int launch_fr_fft(Ctx *c, void *d_data, uint32_t log_n, int inverse, int coset) {
     const size_t bytes = (size_t)32 << log_n;
-    int rc = dev_reserve(c, c->misc, bytes);
+    const bool three = fft_plan(log_n).npass == 3;
+    int rc = dev_reserve(c, c->misc, three ? 2 * bytes : bytes);
     if (rc) return rc;
     void *res = nullptr;
-    if ((rc = fft_run(c, d_data, c->misc.p, log_n, inverse, coset, &res))) return rc;
+    if ((rc = fft_run(c, d_data, c->misc.p, log_n, inverse, coset, &res, three ? (char *)c->misc.p + bytes : nullptr))) return rc;
     if (res != d_data) P2B_CUDA(c, cudaMemcpyAsync(d_data, res, bytes, cudaMemcpyDeviceToDevice, c->stream));
     return P2B_OK;
 }

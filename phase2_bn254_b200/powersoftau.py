@@ -11,6 +11,8 @@ Mirrors (names, argument meaning, error behaviour):
 The maps are numpy uint8 arrays (np.memmap works), exactly the byte layout of the challenge / response files.
 """
 import hashlib
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -136,6 +138,13 @@ def keypair(rng, digest):
     seeds one from OS entropy + user input, compute_constrained.rs:103-141, or from the beacon hash)."""
     assert len(digest) == 64
     tau, alpha, beta = rng.gen_fr(), rng.gen_fr(), rng.gen_fr()
+    return public_key_for(PrivateKey(tau, alpha, beta), rng, digest), PrivateKey(tau, alpha, beta)
+
+
+def public_key_for(key, rng, digest):
+    """The PublicKey half of keypair() for given secrets: three proofs of knowledge (g1_s, g1_s^x, g2_s^x) with g1_s drawn
+    from `rng` and g2_s = hash of (personalization, digest, g1_s, g1_s^x) into G2 (keypair.rs:64-90)."""
+    tau, alpha, beta = key.tau, key.alpha, key.beta
 
     def op(x, personalization):
         g1_s = rng.gen_g1()
@@ -145,8 +154,7 @@ def keypair(rng, digest):
         return (g1_s, g1_s_x), _lib.host_mul(1, g2_s, xb)
 
     pk_tau, pk_alpha, pk_beta = op(tau, 0), op(alpha, 1), op(beta, 2)
-    return (PublicKey(pk_tau[0], pk_alpha[0], pk_beta[0], pk_tau[1], pk_alpha[1], pk_beta[1]),
-            PrivateKey(tau, alpha, beta))
+    return PublicKey(pk_tau[0], pk_alpha[0], pk_beta[0], pk_tau[1], pk_alpha[1], pk_beta[1])
 
 
 def calculate_hash(input_map):
@@ -296,6 +304,18 @@ def verify_transformation(input_map, output_map, key, digest, input_is_compresse
     rng = rng or np.random.default_rng()
     assert len(digest) == 64
     p = parameters
+    # The per-chunk same_ratio checks (two pairings each, ~35 ms on one core) run on host threads while the GPU works on
+    # the next chunk's MSMs (the library call releases the GIL); the verdict is the conjunction, as in the reference.
+    pool = ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
+    try:
+        return _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, input_is_compressed,
+                                      output_is_compressed, check_input_for_correctness, check_output_for_correctness, p)
+    finally:
+        pool.shutdown(wait=False, cancel_futures=True)
+
+
+def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, input_is_compressed, output_is_compressed,
+                           check_input_for_correctness, check_output_for_correctness, p):
     tau_g2_s = compute_g2_s(digest, key.tau_g1[0], key.tau_g1[1], 0)
     alpha_g2_s = compute_g2_s(digest, key.alpha_g1[0], key.alpha_g1[1], 1)
     beta_g2_s = compute_g2_s(digest, key.beta_g1[0], key.beta_g1[1], 2)
@@ -332,12 +352,18 @@ def verify_transformation(input_map, output_map, key, digest, input_is_compresse
     g2_pair = (pt(a_tau2, 0, 128), pt(a_tau2, 1, 128))
     g1_pair = (pt(a_tau, 0, 64), pt(a_tau, 1, 64))
 
-    def powers_ok(group, v, pair):
+    pending = []
+
+    def powers_ok(group, v, pair, wait=False):
         n = v.size // (128 if group else 64)
         if n < 2:
             return False                              # merge_pairs of nothing is (0, 0): same_ratio rejects zero
         s, sx = power_pairs(ctx, group, v, _random_scalars(rng, n - 1))
-        return same_ratio((s, sx), pair) if group == 0 else same_ratio(pair, (s, sx))
+        pending.append(pool.submit(same_ratio, (s, sx), pair) if group == 0 else pool.submit(same_ratio, pair, (s, sx)))
+        done = [f for f in pending if f.done()]
+        if wait:
+            done = list(pending)
+        return all(f.result() for f in done)          # a failed check stops the walk at the next chunk at the latest
 
     last_first = [None, None]
     for start in range(0, p.powers_length, p.batch_size):
@@ -373,7 +399,7 @@ def verify_transformation(input_map, output_map, key, digest, input_is_compresse
             last_first[1] = pt(v, 0, 64)
     if last_first[0] is None or last_first[1] is None:
         return False
-    return powers_ok(0, np.frombuffer(last_first[0] + last_first[1], dtype=np.uint8), g2_pair)
+    return powers_ok(0, np.frombuffer(last_first[0] + last_first[1], dtype=np.uint8), g2_pair, wait=True)
 
 
 BatchedAccumulator.verify_transformation = staticmethod(verify_transformation)
