@@ -30,6 +30,7 @@ static constexpr int FFT_RMAX = 8;        // stages per pass
 #ifndef FFT_REG_STAGES
 #define FFT_REG_STAGES 3                  // last stages of a pass done in registers (3: radix-8 groups, 2: radix-4)
 #endif
+static constexpr uint32_t FFT_DIRECT_LOG = 20;   // largest per-pass twiddle table kept as a direct table (2^20 x 32 B = 32 MB, L2 resident)
 #ifndef FFT_MIN_BLOCKS
 #define FFT_MIN_BLOCKS 3
 #endif
@@ -40,6 +41,7 @@ struct FftPass {
     uint32_t log_n, r, log_ns, log_te;    // tile has 2^log_te elements = 2^(log_te - r) columns x 2^r
     uint32_t lb;                          // bits of the low twiddle table
     const Fr *tlo, *thi, *twr;
+    const Fr *tdir;                       // direct table omega_(Ns R)^e, e < Ns R (null: use the two-level table)
     uint32_t scale[8];                    // LAST, inverse transform: n^-1 in Montgomery form
     uint32_t do_scale;
     unsigned long long *err;
@@ -75,7 +77,9 @@ template <bool FIRST, bool LAST> __global__ void __launch_bounds__(FFT_BLOCK, FF
             if (p.log_ns) {
                 const uint32_t k = (uint32_t)j & ns_mask;
                 const uint32_t ex = (t * k) << (p.log_n - p.log_ns - r);
-                Fr w = mul(p.tlo[ex & ((1u << p.lb) - 1u)], p.thi[ex >> p.lb]);
+                // omega_(Ns R)^(t k): straight from the pass's own table when it is small enough to stay in L2 (one
+                // multiplication per element), else combined from the two-level table of omega_n (two multiplications)
+                Fr w = p.tdir ? p.tdir[t * k] : mul(p.tlo[ex & ((1u << p.lb) - 1u)], p.thi[ex >> p.lb]);
                 v = mul(v, w);
             }
         }
@@ -199,6 +203,13 @@ static __global__ void k_fft_tables(Fr *tlo, Fr *thi, Fr *twr, Fr base, Fr root2
     } else if (twr && i < nlo + nhi + 128) twr[i - nlo - nhi] = pow_u64(root256, i - nlo - nhi);
 }
 
+// dst[e] = base^(e << shift) from the two-level table (thi may be the copy that carries 1/n)
+static __global__ void k_fft_direct_table(Fr *dst, const Fr *tlo, const Fr *thi, uint32_t lb, uint32_t shift, uint32_t count) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t ex = e << shift;
+    dst[e] = mul(tlo[ex & ((1u << lb) - 1u)], thi[ex >> lb]);
+}
 static __global__ void k_fft_scale_table(Fr *dst, const Fr *src, uint32_t n, Fr k) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = mul(src[i], k);
@@ -272,7 +283,12 @@ static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
     if (c->fft_tw.p && c->fft_tw_log_n == log_n && c->fft_tw_inverse == inverse) return P2B_OK;
     const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
     const size_t nent = ((size_t)1 << lb) + ((size_t)1 << hb) + 128;
-    int rc = dev_reserve(c, c->fft_tw, (2 * nent + ((size_t)1 << hb)) * sizeof(Fr));      // [omega tables | coset tables | thi x n^-1]
+    // [omega tables | coset tables | thi x n^-1 | direct tables of the passes whose omega_(Ns R) table has <= 2^FFT_DIRECT_LOG entries]
+    const FftPlan plan = fft_plan(log_n);
+    size_t ndirect = 0;
+    for (uint32_t i = 1, lns = plan.r[0]; i < plan.npass; lns += plan.r[i], i++)
+        if (lns + plan.r[i] <= FFT_DIRECT_LOG) ndirect += (size_t)1 << (lns + plan.r[i]);
+    int rc = dev_reserve(c, c->fft_tw, (2 * nent + ((size_t)1 << hb) + ndirect) * sizeof(Fr));
     if (rc) return rc;
     Fr root = host_root_of_unity(), omega = root, root256 = root;
     for (uint32_t i = log_n; i < 28; i++) omega = sqr(omega);
@@ -288,6 +304,18 @@ static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
     Fr ninv = inverse ? inv(host_fr_from_u64((uint64_t)1 << log_n)) : fp_one<FrP>();
     k_fft_scale_table<<<(int)((((size_t)1 << hb) + 127) / 128), 128, 0, c->stream>>>((Fr *)c->fft_tw.p + 2 * nent, thi, (uint32_t)1 << hb, ninv);
     c->launches += 3;
+    {
+        Fr *dir = (Fr *)c->fft_tw.p + 2 * nent + ((size_t)1 << hb);
+        for (uint32_t i = 1, lns = plan.r[0]; i < plan.npass; lns += plan.r[i], i++) {
+            const uint32_t bits = lns + plan.r[i];
+            if (bits > FFT_DIRECT_LOG) continue;
+            const bool last = i + 1 == plan.npass;
+            k_fft_direct_table<<<(int)((((size_t)1 << bits) + 127) / 128), 128, 0, c->stream>>>(
+                dir, tlo, last ? (const Fr *)((Fr *)c->fft_tw.p + 2 * nent) : (const Fr *)thi, lb, log_n - bits, 1u << bits);
+            c->launches++;
+            dir += (size_t)1 << bits;
+        }
+    }
     P2B_CUDA(c, cudaGetLastError());
     c->fft_tw_log_n = log_n;
     c->fft_tw_inverse = inverse;
@@ -336,6 +364,7 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
     const uint32_t te = 1u << pl.log_te;
     const size_t smem = (size_t)(8 * (te + (te >> 5) + 1) + 8 * 128) * 4;
     const uint32_t blocks = (uint32_t)(n >> pl.log_te);
+    const Fr *dir_next = thi_scaled + ((size_t)1 << hb);             // direct tables, in pass order (fft_tables)
     void *src = d_data, *dst = d_tmp;
     const bool via_tmp2 = d_tmp2 && pl.npass == 3;
     uint32_t log_ns = 0;
@@ -346,6 +375,11 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
         if (last && inverse && !first) {                               // the twiddle at load already carries 1/n
             p.thi = thi_scaled;
             p.do_scale = 0;
+        }
+        p.tdir = nullptr;
+        if (!first && log_ns + pl.r[i] <= FFT_DIRECT_LOG) {
+            p.tdir = dir_next;
+            dir_next += (size_t)1 << (log_ns + pl.r[i]);
         }
         if (first && last) rc = fft_launch_pass<true, true>(c, p, blocks, smem);
         else if (first) rc = fft_launch_pass<true, false>(c, p, blocks, smem);
