@@ -438,16 +438,79 @@ template <class F> __global__ void __launch_bounds__(256) k_msm_reduce2(const ui
     }
 }
 
-// Horner over the windows (most significant first); result as XYZZ (out_xyzz) and as affine wire words (out_wire)
-template <class F> __global__ void k_msm_final(const uint32_t *wsum, MsmGeom g, uint32_t *out_wire) {
-    if (threadIdx.x || blockIdx.x) return;
+// ---- lane-parallel curve operations for the serial Horner chain of k_msm_final -----------------------------------------
+// A chain of 255 dependent doublings on ONE thread occupies a whole warp slot of the multiplier pipe for one lane's worth
+// of work (a lone warp runs a Montgomery multiplication in ~850 cycles whatever the instruction-level parallelism; measured,
+// DESIGN.md section 4).  Here every lane of the warp holds the same point; at each dependency level of the formula lane l
+// computes the l-th independent product and the results are exchanged with shuffles, so a doubling costs 3 multiplication
+// times instead of 9 and an addition 4 instead of 14.  All 32 lanes run the same code (lanes beyond the level's width
+// recompute one of the products), so there is no divergence; every lane returns the same result.
+template <class F> __device__ __forceinline__ F shfl_f(const F &v, int src_lane) {
+    F r;
+#pragma unroll
+    for (int j = 0; j < FieldTraits<F>::WORDS; j++) set_word(r, j, __shfl_sync(0xffffffffu, get_word(v, j), src_lane));
+    return r;
+}
+template <class F> __device__ __forceinline__ Xyzz<F> xdbl_lanes(const Xyzz<F> &p) {
+    const int lane = threadIdx.x & 31;
+    const F u = dbl(p.y);
+    F a = select(lane == 1, p.x, u);                                   // lane 0: u^2 = v, lane 1: x^2
+    F t = mul(a, a);
+    const F v = shfl_f(t, 0), xx = shfl_f(t, 1);
+    const F m = add(dbl(xx), xx);
+    a = select(lane == 1, p.x, select(lane == 2, m, select(lane == 3, p.zz, u)));      // u v = w | x v = s | m m | zz v
+    F b = select(lane == 2, m, v);
+    t = mul(a, b);
+    const F w = shfl_f(t, 0), s = shfl_f(t, 1), mm = shfl_f(t, 2);
+    Xyzz<F> r;
+    r.zz = shfl_f(t, 3);
+    r.x = sub(sub(mm, s), s);
+    a = select(lane == 0, m, w);                                       // m (s - x3) | w y | w zzz
+    b = select(lane == 0, sub(s, r.x), select(lane == 1, p.y, p.zzz));
+    t = mul(a, b);
+    r.y = sub(shfl_f(t, 0), shfl_f(t, 1));
+    r.zzz = shfl_f(t, 2);
+    return r;                                                          // infinity (zz = 0) stays infinity
+}
+template <class F> __device__ __forceinline__ Xyzz<F> xadd_lanes(const Xyzz<F> &p, const Xyzz<F> &q) {
+    const int lane = threadIdx.x & 31;
+    // level 1: x1 zz2 = u1 | x2 zz1 = u2 | y1 zzz2 = s1 | y2 zzz1 = s2 | zz1 zz2 | zzz1 zzz2
+    F a = select(lane == 0, p.x, select(lane == 1, q.x, select(lane == 2, p.y, select(lane == 3, q.y, select(lane == 4, p.zz, p.zzz)))));
+    F b = select(lane == 0, q.zz, select(lane == 1, p.zz, select(lane == 2, q.zzz, select(lane == 3, p.zzz, select(lane == 4, q.zz, q.zzz)))));
+    F t = mul(a, b);
+    const F u1 = shfl_f(t, 0), u2 = shfl_f(t, 1), s1 = shfl_f(t, 2), s2 = shfl_f(t, 3), zz12 = shfl_f(t, 4), zzz12 = shfl_f(t, 5);
+    const F pp_ = sub(u2, u1), rr = sub(s2, s1);
+    a = select(lane == 1, rr, pp_);                                    // P^2 = pp | R^2
+    t = mul(a, a);
+    const F pp = shfl_f(t, 0), rr2 = shfl_f(t, 1);
+    a = select(lane == 0, pp_, select(lane == 1, u1, zz12));           // P pp = ppp | u1 pp = q | zz1 zz2 pp
+    t = mul(a, pp);
+    const F ppp = shfl_f(t, 0), qq = shfl_f(t, 1);
+    Xyzz<F> r;
+    r.zz = shfl_f(t, 2);
+    r.x = sub(sub(sub(rr2, ppp), qq), qq);
+    a = select(lane == 0, rr, select(lane == 1, s1, zzz12));           // R (q - x3) | s1 ppp | zzz1 zzz2 ppp
+    b = select(lane == 0, sub(qq, r.x), ppp);
+    t = mul(a, b);
+    r.y = sub(shfl_f(t, 0), shfl_f(t, 1));
+    r.zzz = shfl_f(t, 2);
+    const bool p_inf = is_zero(p.zz), q_inf = is_zero(q.zz);
+    if (!p_inf & !q_inf & is_zero(pp_) & is_zero(rr)) r = xdbl_lanes(p);     // warp-uniform: every lane holds the same points
+    r = select(q_inf, p, r);
+    return select(p_inf, q, r);
+}
+
+// Horner over the windows (most significant first), one warp (see above); result as affine wire words (out_wire)
+template <class F> __global__ void __launch_bounds__(32) k_msm_final(const uint32_t *wsum, MsmGeom g, uint32_t *out_wire) {
+    if (blockIdx.x) return;
     Xyzz<F> acc = load_xyzz<F>(wsum, g.nwin - 1);
 #pragma unroll 1
     for (int w = (int)g.nwin - 2; w >= 0; w--) {
 #pragma unroll 1
-        for (uint32_t j = 0; j < win_width(g, (uint32_t)w); j++) acc = xdbl(acc);
-        acc = xadd(acc, load_xyzz<F>(wsum, w));
+        for (uint32_t j = 0; j < win_width(g, (uint32_t)w); j++) acc = xdbl_lanes(acc);
+        acc = xadd_lanes(acc, load_xyzz<F>(wsum, w));
     }
+    if (threadIdx.x) return;
     bool inf = is_zero(acc.zz);
     F t = inv(mul(acc.zz, acc.zzz));
     Aff<F> a;
