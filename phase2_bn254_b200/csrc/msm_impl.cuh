@@ -392,49 +392,85 @@ template <class F> __device__ __forceinline__ Xyzz<F> warp_reduce(Xyzz<F> v, boo
     return v;
 }
 
-// one block of 8 warps per window; the tpw strips of the window form tpw/32 rows of 32.  Pass 0: each row is reduced by
-// one warp into P = sum S1, Q = sum l*S1, A = sum S2 (shared memory, 3 x nrows entries).  Pass 1: warp 0 reduces the
-// rows: wp = sum row*P_row, qs = sum Q_row, as = sum A_row.  Then W = as + strip * (32 * wp + qs).
-template <class F> __global__ void __launch_bounds__(256) k_msm_reduce2(const uint32_t *s1, const uint32_t *s2, MsmGeom g, uint32_t *wsum) {
+// RED2_SPLIT blocks of 8 warps per window; the tpw strips of the window form tpw/32 rows of 32.  Pass 0: each row is reduced by
+// one warp (the rows of a window are dealt over its RED2_SPLIT x 8 warps) into P = sum S1, Q = sum l*S1, A = sum S2, written
+// to a per-window scratch in global memory (3 x 32 entries).  The block that finishes last (ticket counter) runs pass 1 on
+// its warp 0: wp = sum row*P_row, qs = sum Q_row, as = sum A_row.  Then W = as + strip * (32 * wp + qs).
+static constexpr uint32_t RED2_SPLIT = 4;
+template <class F> __device__ __forceinline__ Xyzz<F> load_xyzz_cg(const uint32_t *base, size_t i) {      // L2 (written by other blocks)
     constexpr int W = FieldTraits<F>::WORDS;
-    __shared__ __align__(16) uint32_t sm[100 * 4 * W];     // [P | Q | A] rows, then [wp | qs | as] in slots 96..98
-    const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nrows = g.tpw >> 5;
+    const uint4 *s = reinterpret_cast<const uint4 *>(base + i * 4 * W);
+    Xyzz<F> p;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        const uint4 v = __ldcg(s + j);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = 4 * j + k;
+            if (idx < W) set_word(p.x, idx, w4[k]);
+            else if (idx < 2 * W) set_word(p.y, idx - W, w4[k]);
+            else if (idx < 3 * W) set_word(p.zz, idx - 2 * W, w4[k]);
+            else set_word(p.zzz, idx - 3 * W, w4[k]);
+        }
+    }
+    return p;
+}
+template <class F> __global__ void __launch_bounds__(256) k_msm_reduce2(const uint32_t *s1, const uint32_t *s2, MsmGeom g, uint32_t *wsum,
+                                                                        uint32_t *rows, uint32_t *cnt) {
+    constexpr int W = FieldTraits<F>::WORDS;
+    __shared__ __align__(16) uint32_t sm[4 * 4 * W];       // [wp | qs | as]
+    __shared__ uint32_t is_last;
+    const uint32_t w = blockIdx.x / RED2_SPLIT, part = blockIdx.x % RED2_SPLIT;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nrows = g.tpw >> 5;
+    uint32_t *wrows = rows + (size_t)w * 96 * 4 * W;
+    const uint32_t gw = part * 8 + wid, stride = 8 * RED2_SPLIT;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-        // items of this pass for this warp: pass 0 -> (row, kind) for rows wid, wid+8, ..; pass 1 -> kind only (warp 0)
-        const uint32_t nitems = pass == 0 ? 3 * ((nrows + 7 - wid) / 8) : (wid == 0 ? 3u : 0u);
+        // items of this pass for this warp: pass 0 -> (row, kind) for rows gw, gw + stride, ..; pass 1 -> kind only (warp 0 of the last block)
+        const uint32_t nitems = pass == 0 ? (gw < nrows ? 3 * ((nrows - gw + stride - 1) / stride) : 0u) : (wid == 0 ? 3u : 0u);
 #pragma unroll 1
         for (uint32_t it = 0; it < nitems; it++) {
             const uint32_t kind = it % 3;                      // 0: P / wp (weighted in pass 1), 1: Q (weighted in pass 0) / qs, 2: A / as
             Xyzz<F> v;
             bool weighted;
+            uint32_t *dst_base;
             uint32_t dst;
             if (pass == 0) {
-                const uint32_t row = wid + 8 * (it / 3);
+                const uint32_t row = gw + stride * (it / 3);
                 v = load_xyzz<F>(kind == 2 ? s2 : s1, (size_t)w * g.tpw + row * 32 + lane);
                 weighted = kind == 1;
+                dst_base = wrows;
                 dst = kind * 32 + row;
             } else {
-                v = load_xyzz<F>(sm, kind * 32 + lane);
+                v = load_xyzz_cg<F>(wrows, kind * 32 + lane);
                 v = select(lane >= nrows, xyzz_infinity<F>(), v);
                 weighted = kind == 0;
-                dst = 96 + kind;
+                dst_base = sm;
+                dst = kind;
             }
             v = warp_reduce(v, weighted);
-            if (lane == 0) store_xyzz<F>(sm, dst, v);
+            if (lane == 0) store_xyzz<F>(dst_base, dst, v);
         }
-        __syncthreads();
+        if (pass == 0) {
+            __threadfence();                                   // the row results of this block are visible before its ticket
+            __syncthreads();
+            if (threadIdx.x == 0) is_last = atomicAdd(&cnt[w], 1u) == RED2_SPLIT - 1 ? 1u : 0u;
+            __syncthreads();
+            if (!is_last) return;
+            __threadfence();
+        } else __syncthreads();
     }
     if (threadIdx.x == 0) {
-        Xyzz<F> b = load_xyzz<F>(sm, 96);                      // wp
+        Xyzz<F> b = load_xyzz<F>(sm, 0);                       // wp
         uint32_t ls = 0;
         while ((1u << ls) < g.strip) ls++;
 #pragma unroll 1
         for (uint32_t i = 0; i <= 5 + ls; i++) {               // b = strip * (32 * wp + qs)
-            if (i == 5) b = xadd(b, load_xyzz<F>(sm, 97));
+            if (i == 5) b = xadd(b, load_xyzz<F>(sm, 1));
             if (i < 5 + ls) b = xdbl(b);
         }
-        store_xyzz<F>(wsum, w, xadd(load_xyzz<F>(sm, 98), b));
+        store_xyzz<F>(wsum, w, xadd(load_xyzz<F>(sm, 2), b));
     }
 }
 
@@ -555,7 +591,10 @@ template <class F> void msm_launch_heavy_impl(Ctx *c, const uint32_t *aff, const
 template <class F> void msm_launch_reduce_impl(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uint32_t *s1, uint32_t *s2, uint32_t *wsum,
                                                uint32_t *d_out_wire, size_t nred) {
     k_msm_reduce1<F><<<(int)((nred + 127) / 128), 128, 0, c->stream>>>(buckets, g, s1, s2);
-    k_msm_reduce2<F><<<g.nwin, 256, 0, c->stream>>>(s1, s2, g, wsum);
+    // scratch behind wsum (reserved by msm_typed): per-window row results and the ticket counters of k_msm_reduce2
+    uint32_t *rows = wsum + (size_t)g.nwin * 4 * FieldTraits<F>::WORDS, *cnt = rows + (size_t)g.nwin * 96 * 4 * FieldTraits<F>::WORDS;
+    cudaMemsetAsync(cnt, 0, (size_t)g.nwin * 4, c->stream);
+    k_msm_reduce2<F><<<g.nwin * RED2_SPLIT, 256, 0, c->stream>>>(s1, s2, g, wsum, rows, cnt);
     k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
 }
 void msm_launch_heavy_g1(Ctx *c, const uint32_t *aff, const uint32_t *sorted, uint32_t *buckets, const MsmHeavy &hv);
@@ -618,7 +657,7 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     if ((rc = dev_reserve(c, c->msm_b, (4 * nslots + 16 + nslots / SCAN_TILE + 8) * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * cap_n * 4))) return rc;
     const size_t nred = (size_t)g.nwin * g.tpw;
-    if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin) * xy))) return rc;
+    if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin + (size_t)g.nwin * 96) * xy + (size_t)g.nwin * 4 + 64))) return rc;
     uint32_t *aff = (uint32_t *)c->msm_a.p;
     uint32_t *hist = (uint32_t *)c->msm_b.p, *cursor = hist + nslots, *offsets = cursor + nslots;   // offsets: nslots + one per group
     uint32_t *perm = offsets + nslots + 16, *tile_sums = perm + nslots;
