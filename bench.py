@@ -463,9 +463,11 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
         cf[:, 0] &= 0x1f
         bases = np.frombuffer(hl[: nv * 64], dtype=np.uint8)
         ctx.sparse_mul(0, bases, offs[:1025], cols[:3072], cf[:3072].reshape(-1))
-        t0 = time.perf_counter()
-        sp = ctx.sparse_mul(0, bases, offs, cols, cf.reshape(-1))
-        dt = time.perf_counter() - t0
+        dt = 1e9
+        for _ in range(2):                                   # the first full-size call also grows the library's scratch buffers
+            t0 = time.perf_counter()
+            sp = ctx.sparse_mul(0, bases, offs, cols, cf.reshape(-1))
+            dt = min(dt, time.perf_counter() - t0)
         import hashlib as _hl
         out["mpc_new_sparse_mul_2^20"] = {"wall_s": round(dt, 4), "rows": nv, "entries": 3 * nv, "Mentries_per_s": round(3 * nv / dt / 1e6, 2),
                                           "out_blake2b": _hl.blake2b(sp.tobytes()).hexdigest()[:32]}

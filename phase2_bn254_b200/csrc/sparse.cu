@@ -107,21 +107,37 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
         minus_one_be[4 * i] = (uint8_t)(v >> 24); minus_one_be[4 * i + 1] = (uint8_t)(v >> 16);
         minus_one_be[4 * i + 2] = (uint8_t)(v >> 8); minus_one_be[4 * i + 3] = (uint8_t)v;
     }
-    std::vector<uint8_t> kind(nnz);
-    std::vector<uint32_t> src(nnz), gen_cols;
-    std::vector<uint8_t> gen_coeffs;
+    // (first a counting pass: when no entry is trivial the caller's arrays are used as they are)
+    uint64_t ntriv = 0;
     for (uint64_t j = 0; j < nnz; j++) {
         const uint8_t *k = coeffs + 32 * j;
-        if (!memcmp(k, ONE_BE, 32)) { kind[j] = 1; src[j] = cols[j]; }
-        else if (!memcmp(k, minus_one_be, 32)) { kind[j] = 2; src[j] = cols[j]; }
-        else {
-            kind[j] = 0;
-            src[j] = (uint32_t)gen_cols.size();
-            gen_cols.push_back(cols[j]);
-            gen_coeffs.insert(gen_coeffs.end(), k, k + 32);
+        ntriv += (!memcmp(k, ONE_BE, 32) || !memcmp(k, minus_one_be, 32)) ? 1 : 0;
+    }
+    const bool all_general = ntriv == 0;
+    std::vector<uint8_t> kind, gen_coeffs;
+    std::vector<uint32_t> src, gen_cols;
+    if (!all_general) {
+        kind.resize(nnz);
+        src.resize(nnz);
+        gen_cols.resize(nnz - ntriv);
+        gen_coeffs.resize((nnz - ntriv) * 32);
+        uint64_t ng = 0;
+        for (uint64_t j = 0; j < nnz; j++) {
+            const uint8_t *k = coeffs + 32 * j;
+            if (!memcmp(k, ONE_BE, 32)) { kind[j] = 1; src[j] = cols[j]; }
+            else if (!memcmp(k, minus_one_be, 32)) { kind[j] = 2; src[j] = cols[j]; }
+            else {
+                kind[j] = 0;
+                src[j] = (uint32_t)ng;
+                gen_cols[ng] = cols[j];
+                memcpy(&gen_coeffs[32 * ng], k, 32);
+                ng++;
+            }
         }
     }
-    const uint64_t ngen = gen_cols.size();
+    const uint32_t *h_gen_cols = all_general ? cols : gen_cols.data();
+    const uint8_t *h_gen_coeffs = all_general ? coeffs : gen_coeffs.data();
+    const uint64_t ngen = nnz - ntriv;
     P2B_CUDA(c, cudaSetDevice(c->device));
     c->last_error.clear();
     P2B_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream));
@@ -142,8 +158,10 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
     uint32_t *A = (uint32_t *)c->gfft.p, *B = (uint32_t *)((char *)c->gfft.p + b_off), *R = (uint32_t *)((char *)c->gfft.p + r_off);
     if (nnz) {
         P2B_CUDA(c, cudaMemcpyAsync(sin, bases, n_bases * psz, cudaMemcpyHostToDevice, c->stream));
-        P2B_CUDA(c, cudaMemcpyAsync(sin + src_off, src.data(), nnz * 4, cudaMemcpyHostToDevice, c->stream));
-        P2B_CUDA(c, cudaMemcpyAsync(sin + kind_off, kind.data(), nnz, cudaMemcpyHostToDevice, c->stream));
+        if (!all_general) {
+            P2B_CUDA(c, cudaMemcpyAsync(sin + src_off, src.data(), nnz * 4, cudaMemcpyHostToDevice, c->stream));
+            P2B_CUDA(c, cudaMemcpyAsync(sin + kind_off, kind.data(), nnz, cudaMemcpyHostToDevice, c->stream));
+        }
         ScalarSpec sc;
         memset(&sc, 0, sizeof sc);
         if (ngen < nnz) {        // +-P entries read the bases as Montgomery affine points: one checked codec pass over the bases
@@ -151,8 +169,8 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
             if ((rc = launch_batch_mul(c, g2, sin, R, n_bases, sc, P2B_ENC_UNCOMPRESSED, P2B_ENC_RAW_MONT_LE, P2B_CHECK_INPUT, 0))) return rc;
         }
         if (ngen) {
-            P2B_CUDA(c, cudaMemcpyAsync(sin + cols_off, gen_cols.data(), ngen * 4, cudaMemcpyHostToDevice, c->stream));
-            P2B_CUDA(c, cudaMemcpyAsync(sin + coef_off, gen_coeffs.data(), ngen * 32, cudaMemcpyHostToDevice, c->stream));
+            P2B_CUDA(c, cudaMemcpyAsync(sin + cols_off, h_gen_cols, ngen * 4, cudaMemcpyHostToDevice, c->stream));
+            P2B_CUDA(c, cudaMemcpyAsync(sin + coef_off, h_gen_coeffs, ngen * 32, cudaMemcpyHostToDevice, c->stream));
             size_t blocks = (ngen * (WU / 4) + 255) / 256;
             if (blocks > (size_t)c->sm_count * 16) blocks = (size_t)c->sm_count * 16;
             k_sparse_gather<F><<<(int)blocks, 256, 0, c->stream>>>((const uint4 *)sin, (const uint32_t *)(sin + cols_off), ngen, (uint4 *)A);
@@ -189,7 +207,7 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
         if ((rc = dev_reserve(c, c->jac, 3 * nseg * elem))) return rc;
         if ((rc = dev_reserve(c, c->prefix, nseg * elem))) return rc;
         uint32_t *jx = (uint32_t *)c->jac.p, *jy = jx + nseg * W, *jz = jy + nseg * W;
-        if (level == 0)
+        if (level == 0 && !all_general)
             k_segment_sum_entries<F><<<(int)((nseg + 127) / 128), 128, 0, c->stream>>>(A, R, (const uint32_t *)(sin + src_off), (const uint8_t *)(sin + kind_off),
                                                                                     (const uint64_t *)c->stage_in[1].p, nseg, jx, jy, jz);
         else
