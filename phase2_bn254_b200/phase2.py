@@ -219,7 +219,6 @@ def merge_pairs(ctx, v1, v2, rng=None):
 def verify_contribution(before, after, ctx=None, rng=None):
     """verify_contribution(before, after) -> the 64-byte hash of the new contribution (parameters.rs:722-855).
     Raises VerificationError where the reference returns Err(())."""
-    ctx = ctx or _lib.Context(0)
     lb, la = params_layout(before.data), params_layout(after.data)
     raw = lambda m, lay, name: m.data[lay[name][0]: lay[name][0] + lay[name][1] * lay[name][2]]
 
@@ -260,6 +259,7 @@ def verify_contribution(before, after, ctx=None, rng=None):
         from .powersoftau import G2_ONE
         if not _lib.same_ratio((g1_one, delta_after), (G2_ONE, d2a)):
             fail("delta_g2 is inconsistent with delta_g1")
+        ctx = ctx or _lib.Context(0)                                                # only the H / L checks need the GPU
         for name in ("h", "l"):                                                     # updated with delta^-1: ratios reversed
             if not _lib.same_ratio(merge_pairs(ctx, raw(before, lb, name), raw(after, la, name), rng), (d2a, d2b)):
                 fail("%s query was not multiplied by delta^-1" % name)

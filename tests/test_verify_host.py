@@ -1,0 +1,138 @@
+"""CPU: the host logic of the verifier / key-generation / MPCParameters.new mirrors (phase2_bn254_b200/{powersoftau,phase2}.py)
+with the oracle standing in for the GPU calls (MSM, bulk codec): chunk walk and ratio checks of verify_transformation,
+the structural and signature checks of verify_contribution, KeypairAssembly / CSR flattening.  The same flows run on the
+real GPU path in tests/test_gpu_verify.py and tests/test_gpu_phase2_new.py."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from util import G1_GEN, G2_GEN, R_MOD, be
+
+
+class OracleCtx:
+    """The three Context calls the mirrors make, answered by the CPU oracle."""
+
+    def __init__(self, oracle):
+        self.oc = oracle
+
+    def msm(self, group, points, scalars):
+        return self.oc.msm(group, bytes(np.asarray(points)), bytes(np.asarray(scalars)), threads=4)
+
+    def recode(self, group, points, in_enc, out_enc, flags=0, out=None):
+        from phase2_bn254_b200 import lib
+        try:
+            res = self.oc.batch_mul(group, bytes(np.asarray(points)), be(1), in_enc, out_enc, bool(flags & lib.CHECK_INPUT),
+                                    bool(flags & lib.REJECT_INFINITY), threads=4)
+        except self.oc.OracleError as e:
+            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
+        return np.frombuffer(res, dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from phase2_bn254_b200 import lib as L
+    L.load()
+    return L
+
+
+def test_verify_transformation_host_logic(lib, oracle):
+    from phase2_bn254_b200.powersoftau import (CeremonyParams, PrivateKey, PublicKey, calculate_hash, public_key_for,
+                                               verify_transformation)
+    size, batch = 3, 4
+    params = CeremonyParams(size, batch)
+    ctx = OracleCtx(oracle)
+    ch0 = np.frombuffer(oracle.pot_generate_initial(size), dtype=np.uint8)
+    digest = calculate_hash(ch0)
+    key = PrivateKey(0x1234567 % R_MOD, 0x89abcdef % R_MOD, 0x13579bdf % R_MOD)
+    pub = public_key_for(key, lib.ChaChaRng([5] * 8), digest)
+    body = oracle.pot_transform(ch0.tobytes(), size, batch, be(key.tau), be(key.alpha), be(key.beta), threads=4)
+    rs = np.zeros(params.contribution_size, dtype=np.uint8)
+    rs[:len(body)] = np.frombuffer(body, dtype=np.uint8)
+    rs[:64] = np.frombuffer(digest, dtype=np.uint8)
+    pub.write(rs, True, params)
+    assert PublicKey.read(rs, True, params) == pub
+    rng = np.random.default_rng(1)
+    assert verify_transformation(ch0, rs, pub, digest, False, True, True, True, params, ctx=ctx, rng=rng)
+    # a different chunking of the same walk (the verifier's batch size is its own choice)
+    assert verify_transformation(ch0, rs, pub, digest, False, True, False, True, CeremonyParams(size, 8), ctx=ctx, rng=rng)
+    # wrong digest, key of other secrets, tampered elements in both loops and at the intersection
+    assert not verify_transformation(ch0, rs, pub, hashlib.blake2b(b"x").digest(), False, True, False, True, params, ctx=ctx, rng=rng)
+    other = public_key_for(PrivateKey(key.tau + 1, key.alpha, key.beta), lib.ChaChaRng([5] * 8), digest)
+    assert not verify_transformation(ch0, rs, other, digest, False, True, False, True, params, ctx=ctx, rng=rng)
+    foreign = rs[64 + 32 * 2: 64 + 32 * 3].copy()
+    for idx in (5, params.powers_length, params.powers_g1_length - 1):
+        bad = rs.copy()
+        bad[64 + 32 * idx: 64 + 32 * (idx + 1)] = foreign
+        assert not verify_transformation(ch0, bad, pub, digest, False, True, False, True, params, ctx=ctx, rng=rng), idx
+    with pytest.raises(RuntimeError):                                    # the reference panics on a one-element chunk
+        verify_transformation(ch0, rs, pub, digest, False, True, False, True, CeremonyParams(size, 1), ctx=ctx, rng=rng)
+
+
+def _params(lib, m, delta_g1=G1_GEN, delta_g2=G2_GEN):
+    g1 = lambda i: lib.host_mul(0, G1_GEN, be(1000 + i))
+    g2 = lambda i: lib.host_mul(1, G2_GEN, be(2000 + i))
+    body = g1(1) + g1(2) + g2(3) + g2(4) + delta_g1 + delta_g2
+    for n, s, grp in ((2, 10, 0), (m - 1, 20, 0), (m, 40, 0), (2, 60, 0), (2, 70, 0), (2, 80, 1)):
+        body += struct.pack(">I", n) + b"".join((g2 if grp else g1)(s + i) for i in range(n))
+    body += hashlib.blake2b(body).digest()
+    return body + struct.pack(">I", 0)
+
+
+def test_verify_contribution_host_logic(lib, oracle):
+    """A contribution assembled by hand on the host (keypair + host scalar multiplications), verified with the oracle's MSM."""
+    from phase2_bn254_b200.phase2 import MPCParameters, VerificationError, keypair, params_layout, verify_contribution
+    ctx = OracleCtx(oracle)
+    m = 4
+    before = MPCParameters(_params(lib, m))
+    pk, delta = keypair(lib.ChaChaRng([8, 7, 6, 5, 4, 3, 2, 1]), before)
+    assert len(pk) == 384 and 0 < delta < R_MOD
+    lay = params_layout(before.data)
+    dinv = be(pow(delta, -1, R_MOD))
+    after = bytearray(before.data.tobytes())
+    for name in ("h", "l"):
+        off, n, size, _ = lay[name]
+        for i in range(n):
+            after[off + 64 * i: off + 64 * (i + 1)] = lib.host_mul(0, bytes(after[off + 64 * i: off + 64 * (i + 1)]), dinv)
+    o1, o2 = lay["delta_g1"][0], lay["delta_g2"][0]
+    after[o1:o1 + 64] = lib.host_mul(0, bytes(after[o1:o1 + 64]), be(delta))
+    after[o2:o2 + 128] = lib.host_mul(1, bytes(after[o2:o2 + 128]), be(delta))
+    after = bytes(after[:-4]) + struct.pack(">I", 1) + pk
+    rng = np.random.default_rng(2)
+    assert verify_contribution(before, MPCParameters(after), ctx=ctx, rng=rng) == hashlib.blake2b(pk).digest()
+    # structural rejections need no MSM at all (ctx=None: they must fail before the GPU is asked for)
+    with pytest.raises(VerificationError):
+        verify_contribution(before, before, ctx=None, rng=rng)
+    bad = bytearray(after); bad[lay["a"][0] + 5] ^= 1
+    with pytest.raises(VerificationError):
+        verify_contribution(before, MPCParameters(bytes(bad)), ctx=None, rng=rng)
+    bad = bytearray(after); bad[-1] ^= 1                                 # transcript
+    with pytest.raises(VerificationError):
+        verify_contribution(before, MPCParameters(bytes(bad)), ctx=None, rng=rng)
+    bad = bytearray(after); bad[o2:o2 + 128] = before.data[o2:o2 + 128].tobytes()      # delta_g2 not updated
+    with pytest.raises(VerificationError):
+        verify_contribution(before, MPCParameters(bytes(bad)), ctx=None, rng=rng)
+    off = lay["h"][0]
+    bad = bytearray(after); bad[off:off + 64] = before.data[off:off + 64].tobytes()    # one H element not updated
+    with pytest.raises(VerificationError):
+        verify_contribution(before, MPCParameters(bytes(bad)), ctx=ctx, rng=rng)
+
+
+def test_keypair_assembly_and_csr():
+    """keypair_assembly.rs:20-118: every term of the three linear combinations lands in its variable's row with the index of
+    the constraint; coefficients are reduced mod r; rows flatten to CSR in input-then-aux order."""
+    from phase2_bn254_b200.phase2 import KeypairAssembly, _csr
+    cs = KeypairAssembly()
+    one = cs.alloc_input()
+    x = cs.alloc_input()
+    a, b = cs.alloc(), cs.alloc()
+    assert (one, x, a, b) == (("input", 0), ("input", 1), ("aux", 0), ("aux", 1))
+    cs.enforce([(a, 1), (one, -1)], [(b, 3)], [(x, 1)])
+    cs.enforce([(a, 2)], [(a, 2)], [(b, R_MOD + 5)])
+    assert cs.num_constraints == 2 and cs.num_inputs == 2 and cs.num_aux == 2
+    assert cs.at_inputs == [[(R_MOD - 1, 0)], []] and cs.at_aux == [[(1, 0), (2, 1)], []]
+    assert cs.bt_aux == [[(2, 1)], [(3, 0)]] and cs.ct_inputs == [[], [(1, 0)]] and cs.ct_aux == [[], [(5, 1)]]
+    offs, cols, k = _csr(cs.at_inputs + cs.at_aux, col_shift=7)
+    assert offs.tolist() == [0, 1, 1, 3, 3] and cols.tolist() == [7, 7, 8]
+    assert k.tobytes() == be(R_MOD - 1) + be(1) + be(2)
