@@ -201,8 +201,10 @@ class VerificationError(Exception):
     """The `Err(())` of verify_contribution / MPCParameters::verify, with the failed check named."""
 
 
-def merge_pairs(ctx, v1, v2, rng=None):
-    """Random linear combination (sum rho_i v1_i, sum rho_i v2_i) over G1 vectors (phase2/src/utils.rs:59-105): two MSMs."""
+def merge_pairs(ctx, v1, v2, rng=None, scalar_bits=253):
+    """Random linear combination (sum rho_i v1_i, sum rho_i v2_i) over G1 vectors (phase2/src/utils.rs:59-105): two MSMs.
+    `scalar_bits`: see powersoftau._random_scalars (253 = full-size scalars like the reference's Fr::rand)."""
+    from .powersoftau import _random_scalars
     rng = rng or np.random.default_rng()
     n = v1.size // 64
     if n != v2.size // 64:
@@ -210,13 +212,11 @@ def merge_pairs(ctx, v1, v2, rng=None):
     if n == 0:
         zero = bytes([0x40]) + bytes(63)
         return zero, zero
-    rho = np.frombuffer(bytearray(rng.bytes(32 * n)), dtype=np.uint8).reshape(n, 32)
-    rho[:, 0] &= 0x1f                                            # < 2^253 < r
-    rho = rho.reshape(-1)
+    rho = _random_scalars(rng, n, scalar_bits)
     return ctx.msm(0, v1, rho), ctx.msm(0, v2, rho)
 
 
-def verify_contribution(before, after, ctx=None, rng=None):
+def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253):
     """verify_contribution(before, after) -> the 64-byte hash of the new contribution (parameters.rs:722-855).
     Raises VerificationError where the reference returns Err(())."""
     lb, la = params_layout(before.data), params_layout(after.data)
@@ -261,7 +261,7 @@ def verify_contribution(before, after, ctx=None, rng=None):
             fail("delta_g2 is inconsistent with delta_g1")
         ctx = ctx or _lib.Context(0)                                                # only the H / L checks need the GPU
         for name in ("h", "l"):                                                     # updated with delta^-1: ratios reversed
-            if not _lib.same_ratio(merge_pairs(ctx, raw(before, lb, name), raw(after, la, name), rng), (d2a, d2b)):
+            if not _lib.same_ratio(merge_pairs(ctx, raw(before, lb, name), raw(after, la, name), rng, scalar_bits), (d2a, d2b)):
                 fail("%s query was not multiplied by delta^-1" % name)
     except _lib.P2BError as e:
         fail("a point does not decode: %s" % e)

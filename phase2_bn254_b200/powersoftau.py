@@ -287,19 +287,29 @@ def _read_points(ctx, amap, parameters, compressed, checked, name, start, count)
         BatchedAccumulator._raise(e)
 
 
-def _random_scalars(rng, n):
-    """n scalars below 2^253 < r (the reference draws Fr::rand from thread_rng, utils.rs:118-124)."""
-    a = np.frombuffer(bytearray(rng.bytes(32 * n)), dtype=np.uint8).reshape(n, 32)
-    a[:, 0] &= 0x1f
+def _random_scalars(rng, n, bits=253):
+    """n random scalars below 2^bits (32 bytes big-endian each).  The reference draws full-size Fr::rand from thread_rng
+    (utils.rs:118-124); 253 bits (< r) is the faithful default.  bits=128 is an opt-in for big verifications: the soundness
+    error of the random linear combination is 2^-128 instead of 2^-253, the zero top digits never reach a bucket (the MSM
+    does about half the work) and half the random bytes are drawn."""
+    if not 8 <= bits <= 253 or bits % 8 not in (0, 5):
+        raise ValueError("bits must be a multiple of 8, or 253")
+    nbytes = (bits + 7) // 8
+    a = np.zeros((n, 32), dtype=np.uint8)
+    a[:, 32 - nbytes:] = np.frombuffer(rng.bytes(nbytes * n), dtype=np.uint8).reshape(n, nbytes)
+    if bits % 8:
+        a[:, 32 - nbytes] &= (1 << (bits % 8)) - 1
     return a.reshape(-1)
 
 
 def verify_transformation(input_map, output_map, key, digest, input_is_compressed, output_is_compressed,
-                          check_input_for_correctness, check_output_for_correctness, parameters, ctx=None, rng=None):
+                          check_input_for_correctness, check_output_for_correctness, parameters, ctx=None, rng=None,
+                          scalar_bits=253):
     """BatchedAccumulator::verify_transformation (batched_accumulator.rs:279-540): the proofs of knowledge, the ratio
     checks on the first elements, then chunk by chunk `same_ratio(power_pairs(after.*), (tau_g2[0], tau_g2[1]))`.
     power_pairs = two Pippenger MSMs per element type and chunk on the GPU; same_ratio = two pairings on the host.
-    Returns True / False like the reference; a chunk that does not deserialize raises (the reference panics)."""
+    Returns True / False like the reference; a chunk that does not deserialize raises (the reference panics).
+    `scalar_bits`: size of the random coefficients (see _random_scalars; 253 = the reference's full-size scalars)."""
     ctx = ctx or BatchedAccumulator.context()
     rng = rng or np.random.default_rng()
     assert len(digest) == 64
@@ -309,13 +319,14 @@ def verify_transformation(input_map, output_map, key, digest, input_is_compresse
     pool = ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
     try:
         return _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, input_is_compressed,
-                                      output_is_compressed, check_input_for_correctness, check_output_for_correctness, p)
+                                      output_is_compressed, check_input_for_correctness, check_output_for_correctness, p,
+                                      scalar_bits)
     finally:
         pool.shutdown(wait=False, cancel_futures=True)
 
 
 def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, input_is_compressed, output_is_compressed,
-                           check_input_for_correctness, check_output_for_correctness, p):
+                           check_input_for_correctness, check_output_for_correctness, p, scalar_bits):
     tau_g2_s = compute_g2_s(digest, key.tau_g1[0], key.tau_g1[1], 0)
     alpha_g2_s = compute_g2_s(digest, key.alpha_g1[0], key.alpha_g1[1], 1)
     beta_g2_s = compute_g2_s(digest, key.beta_g1[0], key.beta_g1[1], 2)
@@ -358,7 +369,7 @@ def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, i
         n = v.size // (128 if group else 64)
         if n < 2:
             return False                              # merge_pairs of nothing is (0, 0): same_ratio rejects zero
-        s, sx = power_pairs(ctx, group, v, _random_scalars(rng, n - 1))
+        s, sx = power_pairs(ctx, group, v, _random_scalars(rng, n - 1, scalar_bits))
         pending.append(pool.submit(same_ratio, (s, sx), pair) if group == 0 else pool.submit(same_ratio, pair, (s, sx)))
         done = [f for f in pending if f.done()]
         if wait:

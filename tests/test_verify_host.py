@@ -55,8 +55,9 @@ def test_verify_transformation_host_logic(lib, oracle):
     assert PublicKey.read(rs, True, params) == pub
     rng = np.random.default_rng(1)
     assert verify_transformation(ch0, rs, pub, digest, False, True, True, True, params, ctx=ctx, rng=rng)
-    # a different chunking of the same walk (the verifier's batch size is its own choice)
-    assert verify_transformation(ch0, rs, pub, digest, False, True, False, True, CeremonyParams(size, 8), ctx=ctx, rng=rng)
+    # a different chunking of the same walk (the verifier's batch size is its own choice), 128-bit random coefficients
+    assert verify_transformation(ch0, rs, pub, digest, False, True, False, True, CeremonyParams(size, 8), ctx=ctx, rng=rng,
+                                 scalar_bits=128)
     # wrong digest, key of other secrets, tampered elements in both loops and at the intersection
     assert not verify_transformation(ch0, rs, pub, hashlib.blake2b(b"x").digest(), False, True, False, True, params, ctx=ctx, rng=rng)
     other = public_key_for(PrivateKey(key.tau + 1, key.alpha, key.beta), lib.ChaChaRng([5] * 8), digest)
@@ -101,6 +102,7 @@ def test_verify_contribution_host_logic(lib, oracle):
     after = bytes(after[:-4]) + struct.pack(">I", 1) + pk
     rng = np.random.default_rng(2)
     assert verify_contribution(before, MPCParameters(after), ctx=ctx, rng=rng) == hashlib.blake2b(pk).digest()
+    assert verify_contribution(before, MPCParameters(after), ctx=ctx, rng=rng, scalar_bits=128) == hashlib.blake2b(pk).digest()
     # structural rejections need no MSM at all (ctx=None: they must fail before the GPU is asked for)
     with pytest.raises(VerificationError):
         verify_contribution(before, before, ctx=None, rng=rng)
@@ -136,3 +138,14 @@ def test_keypair_assembly_and_csr():
     offs, cols, k = _csr(cs.at_inputs + cs.at_aux, col_shift=7)
     assert offs.tolist() == [0, 1, 1, 3, 3] and cols.tolist() == [7, 7, 8]
     assert k.tobytes() == be(R_MOD - 1) + be(1) + be(2)
+
+
+def test_random_scalars_shape():
+    from phase2_bn254_b200.powersoftau import _random_scalars
+    rng = np.random.default_rng(3)
+    a = _random_scalars(rng, 200, 253).reshape(200, 32)
+    assert a[:, 0].max() <= 0x1f and a[:, 0].max() > 0 and all(int.from_bytes(r.tobytes(), "big") < R_MOD for r in a)
+    b = _random_scalars(rng, 200, 128).reshape(200, 32)
+    assert not b[:, :16].any() and b[:, 16:].any()
+    with pytest.raises(ValueError):
+        _random_scalars(rng, 1, 254)
