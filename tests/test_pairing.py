@@ -211,3 +211,20 @@ def test_phase1_keypair_verifies(lib):
     # same seed, same key (the beacon binaries rely on this)
     pub2, priv2 = keypair(lib.ChaChaRng.from_digest(hashlib.sha256(b"seed").digest()), digest)
     assert pub2 == pub and priv2 == priv
+
+
+def test_keygen_regression_vectors(lib):
+    """tests/golden/keygen_selfgen.json: SELF-GENERATED vectors (tools/make_keygen_golden.py) -- they pin the host RNG path
+    against accidental change; they are not reference output (no reference vector exists for this path in-tree)."""
+    import json
+    import os
+    from phase2_bn254_b200.powersoftau import keypair
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "keygen_selfgen.json")))
+    rng = lib.ChaChaRng(g["seed"])
+    assert [hex(rng.gen_fr()) for _ in range(3)] == g["fr"]
+    assert rng.gen_g1().hex() == g["g1"] and rng.gen_g2().hex() == g["g2"] and rng.next_u32() == g["u32_after"]
+    assert lib.hash_to_g2(bytes(range(32))).hex() == g["hash_to_g2_of_0_to_31"]
+    k = g["phase1_keypair"]
+    pub, priv = keypair(lib.ChaChaRng.from_digest(hashlib.sha256(b"golden seed").digest()), bytes.fromhex(k["digest"]))
+    assert (hex(priv.tau), hex(priv.alpha), hex(priv.beta)) == (k["tau"], k["alpha"], k["beta"])
+    assert hashlib.blake2b(pub.serialize()).hexdigest() == k["public_key_blake2b"]
