@@ -79,6 +79,38 @@ def sharded_msm(ctx, group_id, local_points, local_scalars, n_local, group=None,
     return ctx.sum_points(group_id, np.frombuffer(parts, dtype=np.uint8))
 
 
+def sharded_merge_pairs(ctx, v1, v2, rank, world, rng=None, scalar_bits=253, group=None, device=None):
+    """merge_pairs (phase2/src/utils.rs:59-105) with the index range split across ranks: every rank combines its slice of
+    the two G1 vectors with its own random coefficients (two MSMs on its GPU); the ranks all-gather the 2 x 64-byte partial
+    results and each adds them up.  The random coefficients need not be shared: the check is a random linear combination
+    per element either way.  Every rank returns the same (s, sx)."""
+    from .powersoftau import _random_scalars
+    rng = rng or np.random.default_rng()
+    v1, v2 = _lib._host(v1), _lib._host(v2)
+    n = v1.size // 64
+    if n != v2.size // 64:
+        raise ValueError("merge_pairs: length mismatch")
+    lo, hi = shard_range(n, rank, world)
+    zero = bytes([0x40]) + bytes(63)
+    if hi > lo:
+        rho = _random_scalars(rng, hi - lo, scalar_bits)
+        part = ctx.msm(0, v1[lo * 64: hi * 64], rho) + ctx.msm(0, v2[lo * 64: hi * 64], rho)
+    else:
+        part = zero + zero
+    parts = np.frombuffer(all_gather_bytes(part, group=group, device=device), dtype=np.uint8).reshape(-1, 2, 64)
+    return (bytes(ctx.sum_points(0, np.ascontiguousarray(parts[:, 0]).reshape(-1))),
+            bytes(ctx.sum_points(0, np.ascontiguousarray(parts[:, 1]).reshape(-1))))
+
+
+def sharded_verify_contribution(ctx, before, after, rank, world, rng=None, scalar_bits=253, group=None, device=None):
+    """phase2 verify_contribution with the H / L random linear combinations sharded over the ranks (the cheap checks --
+    transcript, signatures of knowledge, delta ratios -- run on every rank).  Every rank returns the contribution hash or
+    raises VerificationError."""
+    from .phase2 import verify_contribution
+    return verify_contribution(before, after, ctx=ctx, rng=rng, scalar_bits=scalar_bits,
+                               merge=lambda a, b: sharded_merge_pairs(ctx, a, b, rank, world, rng, scalar_bits, group, device))
+
+
 def sharded_transform(ctx, input_map, output_map, parameters, key, rank, world, input_is_compressed=False,
                       compress_the_output=True, check_input_for_correctness=False):
     """BatchedAccumulator::transform with every section split across `world` ranks (no collective: rank r writes
@@ -89,4 +121,5 @@ def sharded_transform(ctx, input_map, output_map, parameters, key, rank, world, 
                                  shard_count=world)
 
 
-__all__ = ["shard_range", "bind_to_gpu_numa", "all_gather_bytes", "sharded_msm", "sharded_transform", "_lib"]
+__all__ = ["shard_range", "bind_to_gpu_numa", "all_gather_bytes", "sharded_msm", "sharded_merge_pairs",
+           "sharded_verify_contribution", "sharded_transform", "_lib"]

@@ -216,9 +216,10 @@ def merge_pairs(ctx, v1, v2, rng=None, scalar_bits=253):
     return ctx.msm(0, v1, rho), ctx.msm(0, v2, rho)
 
 
-def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253):
+def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253, merge=None):
     """verify_contribution(before, after) -> the 64-byte hash of the new contribution (parameters.rs:722-855).
-    Raises VerificationError where the reference returns Err(())."""
+    Raises VerificationError where the reference returns Err(()).  `merge(v1, v2) -> (s, sx)` replaces the local merge_pairs
+    (dist.sharded_verify_contribution passes the multi-GPU one)."""
     lb, la = params_layout(before.data), params_layout(after.data)
     raw = lambda m, lay, name: m.data[lay[name][0]: lay[name][0] + lay[name][1] * lay[name][2]]
 
@@ -259,9 +260,11 @@ def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253):
         from .powersoftau import G2_ONE
         if not _lib.same_ratio((g1_one, delta_after), (G2_ONE, d2a)):
             fail("delta_g2 is inconsistent with delta_g1")
-        ctx = ctx or _lib.Context(0)                                                # only the H / L checks need the GPU
+        if merge is None:
+            ctx = ctx or _lib.Context(0)                                            # only the H / L checks need the GPU
+            merge = lambda a, b: merge_pairs(ctx, a, b, rng, scalar_bits)
         for name in ("h", "l"):                                                     # updated with delta^-1: ratios reversed
-            if not _lib.same_ratio(merge_pairs(ctx, raw(before, lb, name), raw(after, la, name), rng, scalar_bits), (d2a, d2b)):
+            if not _lib.same_ratio(merge(raw(before, lb, name), raw(after, la, name)), (d2a, d2b)):
                 fail("%s query was not multiplied by delta^-1" % name)
     except _lib.P2BError as e:
         fail("a point does not decode: %s" % e)

@@ -63,6 +63,51 @@ def test_sharded_msm_world2():
         assert gathered == bytes([0]) * 64 + bytes([1]) * 64
 
 
+def _verify_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch.distributed as dist
+    import oracle as oc
+    from phase2_bn254_b200 import dist as pdist, lib
+    from phase2_bn254_b200.phase2 import MPCParameters, VerificationError
+    from test_verify_host import contribution_by_hand
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        lib.load()
+        before, after, expected, lay = contribution_by_hand(lib, 7)          # h = 6, l = 7 points: uneven shards
+        ctx = OracleCtx(oc)
+        got = pdist.sharded_verify_contribution(ctx, before, MPCParameters(after), rank, world, rng=np.random.default_rng(10 + rank))
+        off = lay["l"][0] + 64 * 6                                           # an element of the LAST rank's slice left as it was
+        bad = bytearray(after)
+        bad[off:off + 64] = before.data[off:off + 64].tobytes()
+        try:
+            pdist.sharded_verify_contribution(ctx, before, MPCParameters(bytes(bad)), rank, world, rng=np.random.default_rng(20 + rank))
+            rejected = False
+        except VerificationError:
+            rejected = True
+        q.put((rank, got == expected, rejected))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_verify_contribution_world2():
+    """The verifier's H / L random linear combinations sharded over two ranks (own random coefficients per rank, all-gather
+    of the 2 x 64-byte partials): both ranks accept the hand-made contribution and both reject a tampered one."""
+    world, port = 2, 30100 + os.getpid() % 500
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_verify_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(out) == [(0, True, True), (1, True, True)]
+
+
 def test_shard_range_partition():
     sys.path.insert(0, ROOT)
     from phase2_bn254_b200.dist import shard_range

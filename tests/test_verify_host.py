@@ -81,11 +81,9 @@ def _params(lib, m, delta_g1=G1_GEN, delta_g2=G2_GEN):
     return body + struct.pack(">I", 0)
 
 
-def test_verify_contribution_host_logic(lib, oracle):
-    """A contribution assembled by hand on the host (keypair + host scalar multiplications), verified with the oracle's MSM."""
-    from phase2_bn254_b200.phase2 import MPCParameters, VerificationError, keypair, params_layout, verify_contribution
-    ctx = OracleCtx(oracle)
-    m = 4
+def contribution_by_hand(lib, m):
+    """(before, after bytes, contribution hash, layout): keypair() + host scalar multiplications, no GPU."""
+    from phase2_bn254_b200.phase2 import MPCParameters, keypair, params_layout
     before = MPCParameters(_params(lib, m))
     pk, delta = keypair(lib.ChaChaRng([8, 7, 6, 5, 4, 3, 2, 1]), before)
     assert len(pk) == 384 and 0 < delta < R_MOD
@@ -100,6 +98,16 @@ def test_verify_contribution_host_logic(lib, oracle):
     after[o1:o1 + 64] = lib.host_mul(0, bytes(after[o1:o1 + 64]), be(delta))
     after[o2:o2 + 128] = lib.host_mul(1, bytes(after[o2:o2 + 128]), be(delta))
     after = bytes(after[:-4]) + struct.pack(">I", 1) + pk
+    return before, after, hashlib.blake2b(pk).digest(), lay
+
+
+def test_verify_contribution_host_logic(lib, oracle):
+    """A contribution assembled by hand on the host (keypair + host scalar multiplications), verified with the oracle's MSM."""
+    from phase2_bn254_b200.phase2 import MPCParameters, VerificationError, verify_contribution
+    ctx = OracleCtx(oracle)
+    before, after, expected, lay = contribution_by_hand(lib, 4)
+    pk = after[-384:]
+    o1, o2 = lay["delta_g1"][0], lay["delta_g2"][0]
     rng = np.random.default_rng(2)
     assert verify_contribution(before, MPCParameters(after), ctx=ctx, rng=rng) == hashlib.blake2b(pk).digest()
     assert verify_contribution(before, MPCParameters(after), ctx=ctx, rng=rng, scalar_bits=128) == hashlib.blake2b(pk).digest()
