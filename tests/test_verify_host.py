@@ -157,3 +157,69 @@ def test_random_scalars_shape():
     assert not b[:, :16].any() and b[:, 16:].any()
     with pytest.raises(ValueError):
         _random_scalars(rng, 1, 254)
+
+
+def test_mpc_parameters_new_host_logic(lib, oracle):
+    """MPCParameters.new orchestration (radix-file parsing, ONE input + x*0=0 constraints, the ext = A.beta + B.alpha + C.coeffs
+    concatenation, filtering, cs_hash, layout) with the oracle's eval restatement standing in for p2b_g{1,2}_sparse_mul."""
+    from phase2_bn254_b200.phase2 import KeypairAssembly, MPCParameters, SynthesisError, params_layout
+
+    class Ctx(OracleCtx):
+        def sparse_mul(self, group, bases, row_offsets, cols, coeffs):
+            return np.frombuffer(self.oc.sparse_mul(group, bytes(np.asarray(bases)), list(row_offsets), list(cols),
+                                                    bytes(np.asarray(coeffs))), dtype=np.uint8)
+
+    m = 8
+    g1 = lambda i: lib.host_mul(0, G1_GEN, be(500 + i))
+    g2 = lambda i: lib.host_mul(1, G2_GEN, be(700 + i))
+    coeffs_g1 = [g1(i) for i in range(m)]
+    coeffs_g2 = [g2(i) for i in range(m)]
+    alpha_c = [g1(100 + i) for i in range(m)]
+    beta_c = [g1(200 + i) for i in range(m)]
+    h = [g1(300 + i) for i in range(m - 1)]
+    radix = g1(1) + g1(2) + g2(3) + b"".join(coeffs_g1) + b"".join(coeffs_g2) + b"".join(alpha_c) + b"".join(beta_c) + b"".join(h)
+    assert len(radix) == 192 + 384 * m
+
+    def circuit(cs):                      # x * y = z ; (z + 1) * 1 = out ; y is used only in B
+        out = cs.alloc_input()
+        x, y, z = cs.alloc(), cs.alloc(), cs.alloc()
+        one = ("input", 0)
+        cs.enforce([(x, 1)], [(y, 1)], [(z, 1)])
+        cs.enforce([(z, 1), (one, 1)], [(one, 1)], [(out, 1)])
+        cs.enforce([(x, 3)], [(one, R_MOD - 2)], [(x, R_MOD - 6)])
+
+    ctx = Ctx(oracle)
+    seen = []
+    p = MPCParameters.new(circuit, False, lambda exp: (seen.append(exp), radix)[1], ctx=ctx)
+    assert seen == [3]                                                   # 3 + 2 input constraints = 5 -> m = 8
+    lay = params_layout(p.data)
+    assert (lay["ic"][1], lay["l"][1], lay["a"][1], lay["b_g1"][1], lay["b_g2"][1], lay["h"][1]) == (2, 3, 5, 5, 5, m - 1)
+    sec = lambda name: p.section(name).tobytes()
+    assert sec("alpha_g1") == g1(1) and sec("beta_g1") == g1(2) and sec("beta_g2") == g2(3) and sec("h") == b"".join(h)
+    assert sec("delta_g1") == G1_GEN and sec("gamma_g2") == G2_GEN and sec("delta_g2") == G2_GEN
+    pm = lambda pt, k: oracle.point_mul(0, pt, be(k % R_MOD))
+    add = lambda *pts: oracle.sum_points(0, b"".join(pts))
+    # variable order: ONE, out, x, y, z.  A rows: ONE {c1:1, c3(input constraint 0):1}, out {c4:1}, x {c0:1, c2:3}, y {}, z {c1:1}
+    a = sec("a")
+    assert a[0:64] == add(coeffs_g1[1], coeffs_g1[3]) and a[64:128] == coeffs_g1[4]
+    assert a[128:192] == add(coeffs_g1[0], pm(coeffs_g1[2], 3))
+    assert a[192:256] == bytes([0x40]) + bytes(63) and a[256:320] == coeffs_g1[1]
+    # ext for x (an aux variable -> l[0]): A.beta {c0:1, c2:3} + B.alpha {} + C.coeffs {c2:-6}
+    assert sec("l")[:64] == add(beta_c[0], pm(beta_c[2], 3), pm(coeffs_g1[2], -6))
+    # ext for out (an input -> ic[1]): A.beta {c4:1} + C.coeffs {c1:1}
+    assert sec("ic")[64:128] == add(beta_c[4], coeffs_g1[1])
+    assert sec("cs_hash") == hashlib.blake2b(p.data[:lay["cs_hash"][0]].tobytes()).digest()
+    # filtering drops the infinity of y out of A; in B only ONE (constraints 1, 2) and y (constraint 0) appear
+    pf = MPCParameters.new(circuit, True, lambda exp: radix, ctx=ctx)
+    layf = params_layout(pf.data)
+    assert (layf["a"][1], layf["b_g1"][1], layf["b_g2"][1]) == (4, 2, 2)
+    assert pf.section("b_g1").tobytes() == add(coeffs_g1[1], pm(coeffs_g1[2], -2)) + coeffs_g1[0]
+    assert pf.section("b_g2").tobytes()[128:] == coeffs_g2[0]
+    # an aux variable that appears nowhere
+    def loose(cs):
+        circuit(cs)
+        cs.alloc()
+    with pytest.raises(SynthesisError):
+        MPCParameters.new(loose, False, lambda exp: radix, ctx=ctx)
+    with pytest.raises(IOError):
+        MPCParameters.new(circuit, False, lambda exp: radix[:-1], ctx=ctx)
