@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libp2b_oracle.so")
 
 G1, G2 = 0, 1
-UNCOMPRESSED, COMPRESSED = 0, 1
+UNCOMPRESSED, COMPRESSED, RAW_MONT_LE = 0, 1, 2
 OK, EARG, EDECODE, EINFINITY_IN, EINFINITY_OUT = 0, 1, 2, 3, 4
 D_NOT_ON_CURVE, D_COORD, D_UNEXPECTED_INFO, D_UNEXPECTED_COMPRESSION = 1, 2, 3, 4
 
@@ -53,6 +53,17 @@ class OracleError(Exception):
 
 def _cbuf(b):
     return (ctypes.c_uint8 * len(b)).from_buffer_copy(b) if len(b) else (ctypes.c_uint8 * 1)()
+
+
+def _cin(b):
+    """Read-only input: contiguous numpy arrays are passed by pointer (no copy: the 2^26-term MSM inputs are 6.4 GB)."""
+    try:
+        import numpy as np
+        if isinstance(b, np.ndarray) and b.flags.c_contiguous and b.dtype == np.uint8 and b.size:
+            return ctypes.c_void_p(b.ctypes.data)
+    except ImportError:
+        pass
+    return _cbuf(b)
 
 
 def batch_mul(group, points, scalars, in_enc=UNCOMPRESSED, out_enc=UNCOMPRESSED, checked=False,
@@ -120,7 +131,7 @@ def pot_transform(challenge, size_log2, batch_size, tau, alpha, beta, in_compres
 def msm(group, points, scalars, threads=1):
     n = len(scalars) // 32
     out = (ctypes.c_uint8 * point_size(group, UNCOMPRESSED))()
-    rc = lib().orc_msm(group, _cbuf(points), _cbuf(scalars), ctypes.c_size_t(n), out, threads)
+    rc = lib().orc_msm(group, _cin(points), _cin(scalars), ctypes.c_size_t(n), out, threads)
     if rc:
         raise OracleError(rc)
     return bytes(out)

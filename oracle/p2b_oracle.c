@@ -97,7 +97,8 @@ enum {
     /* decode sub-codes, GroupDecodingError pairing/src/lib.rs:280-291 */
     ORC_D_NOT_ON_CURVE = 1, ORC_D_COORD = 2, ORC_D_UNEXPECTED_INFO = 3, ORC_D_UNEXPECTED_COMPRESSION = 4
 };
-enum { ENC_UNCOMPRESSED = 0, ENC_COMPRESSED = 1 };
+enum { ENC_UNCOMPRESSED = 0, ENC_COMPRESSED = 1, ENC_RAW_MONT_LE = 2 };
+static int enc_bytes(int g2, int enc) { int full = g2 ? 128 : 64; return enc == ENC_COMPRESSED ? full / 2 : full; }
 
 /* ---- codecs ---- */
 static int all_zero(const uint8_t *b, int n) { uint8_t a = 0; for (int i = 0; i < n; i++) a |= b[i]; return a == 0; }
@@ -118,8 +119,36 @@ static int g2_on_curve(const g2_aff *p) {
     fq2 b = g2_b(); fq2_add(&x3, &b);
     return fq2_eq(&y2, &x3);
 }
+/* RawEncodable (pairing/src/bn256/ec.rs:653-706): coordinates as Montgomery limbs, little-endian (`into_raw_repr().write_le`),
+ * all-zero bytes = the point at infinity; `from_raw_repr` rejects limbs >= q (CoordinateDecodingError). */
+static int fq_read_raw(fq *out, const uint8_t *b) {
+    for (int i = 0; i < 4; i++) { uint64_t v = 0; for (int j = 7; j >= 0; j--) v = (v << 8) | b[8 * i + j]; out->l[i] = v; }
+    return r_cmp(out->l, FQ.m) < 0;
+}
+static void fq_write_raw(const fq *a, uint8_t *b) {
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) b[8 * i + j] = (uint8_t)(a->l[i] >> (8 * j));
+}
+static int g1_on_curve(const g1_aff *p);
+static int g2_on_curve(const g2_aff *p);
+static int g1_decode_raw(g1_aff *out, const uint8_t *src, int checked) {
+    if (all_zero(src, 64)) { *out = g1_aff_zero(); return 0; }
+    out->inf = 0;
+    if (!fq_read_raw(&out->x, src) || !fq_read_raw(&out->y, src + 32)) return ORC_D_COORD;
+    if (checked && !g1_on_curve(out)) return ORC_D_NOT_ON_CURVE;      /* from_raw_uncompressed_le, ec.rs:696-704 */
+    return 0;
+}
+/* G2 has no RawEncodable impl in the reference; include/p2b.h defines the same layout over x.c0, x.c1, y.c0, y.c1 */
+static int g2_decode_raw(g2_aff *out, const uint8_t *src, int checked) {
+    if (all_zero(src, 128)) { *out = g2_aff_zero(); return 0; }
+    out->inf = 0;
+    if (!fq_read_raw(&out->x.c0, src) || !fq_read_raw(&out->x.c1, src + 32) || !fq_read_raw(&out->y.c0, src + 64) ||
+        !fq_read_raw(&out->y.c1, src + 96)) return ORC_D_COORD;
+    if (checked && !g2_on_curve(out)) return ORC_D_NOT_ON_CURVE;
+    return 0;
+}
 /* returns 0 or a decode sub-code */
 static int g1_decode(g1_aff *out, const uint8_t *src, int enc, int checked) {
+    if (enc == ENC_RAW_MONT_LE) return g1_decode_raw(out, src, checked);
     int n = enc == ENC_COMPRESSED ? 32 : 64;
     uint8_t b[64]; memcpy(b, src, n);
     if (b[0] & 0x40) {
@@ -152,6 +181,7 @@ static int g1_decode(g1_aff *out, const uint8_t *src, int enc, int checked) {
 static void g1_encode(const g1_aff *p, uint8_t *dst, int enc) {
     int n = enc == ENC_COMPRESSED ? 32 : 64;
     memset(dst, 0, n);
+    if (enc == ENC_RAW_MONT_LE) { if (!p->inf) { fq_write_raw(&p->x, dst); fq_write_raw(&p->y, dst + 32); } return; }
     if (p->inf) { dst[0] |= 0x40; return; }
     fq_write(&p->x, dst);
     if (enc == ENC_UNCOMPRESSED) { fq_write(&p->y, dst + 32); return; }
@@ -159,6 +189,7 @@ static void g1_encode(const g1_aff *p, uint8_t *dst, int enc) {
     if (fq_gt(&p->y, &negy)) dst[0] |= 0x80;
 }
 static int g2_decode(g2_aff *out, const uint8_t *src, int enc, int checked) {
+    if (enc == ENC_RAW_MONT_LE) return g2_decode_raw(out, src, checked);
     int n = enc == ENC_COMPRESSED ? 64 : 128;
     uint8_t b[128]; memcpy(b, src, n);
     if (enc == ENC_UNCOMPRESSED && (b[0] & 0x80)) return ORC_D_UNEXPECTED_COMPRESSION;
@@ -188,6 +219,10 @@ static int g2_decode(g2_aff *out, const uint8_t *src, int enc, int checked) {
 static void g2_encode(const g2_aff *p, uint8_t *dst, int enc) {
     int n = enc == ENC_COMPRESSED ? 64 : 128;
     memset(dst, 0, n);
+    if (enc == ENC_RAW_MONT_LE) {
+        if (!p->inf) { fq_write_raw(&p->x.c0, dst); fq_write_raw(&p->x.c1, dst + 32); fq_write_raw(&p->y.c0, dst + 64); fq_write_raw(&p->y.c1, dst + 96); }
+        return;
+    }
     if (p->inf) { dst[0] |= 0x40; return; }
     fq_write(&p->x.c1, dst); fq_write(&p->x.c0, dst + 32);
     if (enc == ENC_UNCOMPRESSED) { fq_write(&p->y.c1, dst + 64); fq_write(&p->y.c0, dst + 96); return; }
@@ -238,8 +273,7 @@ static void bexp_range(void *vp, size_t lo, size_t hi, int tid) {
     (void)tid;
     bexp_ctx *c = (bexp_ctx *)vp;
     size_t m = hi - lo;
-    int isz = c->g2 ? (c->in_enc ? 64 : 128) : (c->in_enc ? 32 : 64);
-    int osz = c->g2 ? (c->out_enc ? 64 : 128) : (c->out_enc ? 32 : 64);
+    int isz = enc_bytes(c->g2, c->in_enc), osz = enc_bytes(c->g2, c->out_enc);
     if (!c->g2) {
         g1_jac *proj = (g1_jac *)malloc(m * sizeof(g1_jac));
         fq *scratch = (fq *)malloc(m * sizeof(fq));

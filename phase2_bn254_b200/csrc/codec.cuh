@@ -105,6 +105,9 @@ P2B_HD bool coord_from_wire(Fq2 &out, const uint32_t *w, uint32_t mask0) {
 P2B_HD void coord_to_wire(const Fq &a, uint32_t *w) { fq_to_wire(a, w); }
 P2B_HD void coord_to_wire(const Fq2 &a, uint32_t *w) { fq_to_wire(a.c1, w); fq_to_wire(a.c0, w + 8); }
 
+P2B_HD bool raw_in_field(const Fq &a) { return is_canonical(a); }
+P2B_HD bool raw_in_field(const Fq2 &a) { return is_canonical(a.c0) & is_canonical(a.c1); }
+
 // ---- decode -----------------------------------------------------------------------------------------------------------
 // w: the encoding as native words (wire_words<F>(enc) of them).  On success fills p / inf.  `check` = is_on_curve for
 // uncompressed input (CheckForCorrectness::Yes).  Returns a DEC_* code.
@@ -120,6 +123,7 @@ template <class F> P2B_HD int point_decode(Aff<F> &p, bool &inf, const uint32_t 
         for (int i = 0; i < n; i++) any |= w[i];
         if (!any) { inf = true; return DEC_OK; }
         for (int i = 0; i < FieldTraits<F>::WORDS; i++) { set_word(p.x, i, w[i]); set_word(p.y, i, w[FieldTraits<F>::WORDS + i]); }
+        if (!(raw_in_field(p.x) & raw_in_field(p.y))) return DEC_COORD;        // Fq::from_raw_repr rejects limbs >= q
         if (check && !on_curve(p)) return DEC_NOT_ON_CURVE;
         return DEC_OK;
     }

@@ -68,36 +68,62 @@ def all_gather_bytes(payload, group=None, device=None):
     return out.cpu().numpy().tobytes()
 
 
+def _gather_with_status(payload, error, group=None, device=None):
+    """All-gather of `payload` prefixed with a status byte.  A rank whose local GPU call failed still takes part in the
+    collective (otherwise the other ranks would wait in it for ever) and flags the failure; afterwards EVERY rank raises,
+    so the ranks also agree on the verdict.  Returns the payloads (status bytes stripped) as one (world, len) array."""
+    size = len(payload)
+    parts = np.frombuffer(all_gather_bytes(bytes([1 if error is None else 0]) + bytes(payload), group=group, device=device),
+                          dtype=np.uint8).reshape(-1, 1 + size)
+    bad = np.nonzero(parts[:, 0] == 0)[0]
+    if bad.size:
+        if error is not None:
+            raise error
+        raise _lib.P2BError(_lib.EDECODE, "rank %d failed on its shard" % int(bad[0]))
+    return parts[:, 1:]
+
+
 def sharded_msm(ctx, group_id, local_points, local_scalars, n_local, group=None, device=None, on_device=False):
     """sum over ALL ranks' terms of scalar * point.  Each rank passes only its own shard (host buffers, or device
     pointers with on_device=True); every rank returns the same uncompressed wire point."""
-    if on_device:
-        part = ctx.msm_dev(group_id, local_points, local_scalars, n_local)
-    else:
-        part = ctx.msm(group_id, local_points, local_scalars)
-    parts = all_gather_bytes(part, group=group, device=device)
-    return ctx.sum_points(group_id, np.frombuffer(parts, dtype=np.uint8))
+    size = _lib.enc_size(group_id, _lib.ENC_UNCOMPRESSED)
+    part, err = bytes(size), None
+    try:
+        if on_device:
+            part = ctx.msm_dev(group_id, local_points, local_scalars, n_local)
+        else:
+            pts, sc = _lib._host(local_points), _lib._host(local_scalars)
+            if sc.size != 32 * n_local or pts.size != size * n_local:
+                raise ValueError("sharded_msm: shard of %d terms needs %d point and %d scalar bytes" % (n_local, size * n_local,
+                                                                                                    32 * n_local))
+            part = ctx.msm(group_id, pts, sc)
+    except (_lib.P2BError, ValueError) as e:
+        err = e
+    parts = _gather_with_status(part, err, group=group, device=device)
+    return ctx.sum_points(group_id, np.ascontiguousarray(parts).reshape(-1))
 
 
 def sharded_merge_pairs(ctx, v1, v2, rank, world, rng=None, scalar_bits=253, group=None, device=None):
     """merge_pairs (phase2/src/utils.rs:59-105) with the index range split across ranks: every rank combines its slice of
     the two G1 vectors with its own random coefficients (two MSMs on its GPU); the ranks all-gather the 2 x 64-byte partial
     results and each adds them up.  The random coefficients need not be shared: the check is a random linear combination
-    per element either way.  Every rank returns the same (s, sx)."""
-    from .powersoftau import _random_scalars
-    rng = rng or np.random.default_rng()
+    per element either way.  Every rank returns the same (s, sx); a decode failure on one rank's shard raises on all."""
+    from .powersoftau import _random_scalars, system_rng
+    rng = rng or system_rng()
     v1, v2 = _lib._host(v1), _lib._host(v2)
     n = v1.size // 64
     if n != v2.size // 64:
         raise ValueError("merge_pairs: length mismatch")
     lo, hi = shard_range(n, rank, world)
     zero = bytes([0x40]) + bytes(63)
+    part, err = zero + zero, None
     if hi > lo:
         rho = _random_scalars(rng, hi - lo, scalar_bits)
-        part = ctx.msm(0, v1[lo * 64: hi * 64], rho) + ctx.msm(0, v2[lo * 64: hi * 64], rho)
-    else:
-        part = zero + zero
-    parts = np.frombuffer(all_gather_bytes(part, group=group, device=device), dtype=np.uint8).reshape(-1, 2, 64)
+        try:
+            part = ctx.msm(0, v1[lo * 64: hi * 64], rho) + ctx.msm(0, v2[lo * 64: hi * 64], rho)
+        except _lib.P2BError as e:
+            err = e
+    parts = _gather_with_status(part, err, group=group, device=device).reshape(-1, 2, 64)
     return (bytes(ctx.sum_points(0, np.ascontiguousarray(parts[:, 0]).reshape(-1))),
             bytes(ctx.sum_points(0, np.ascontiguousarray(parts[:, 1]).reshape(-1))))
 

@@ -356,6 +356,9 @@ class Context:
     def msm(self, group, points, scalars):
         pts, sc = _host(points), _host(scalars)
         n = sc.size // 32
+        if sc.size % 32 or pts.size != n * enc_size(group, ENC_UNCOMPRESSED):
+            raise ValueError("msm: %d scalar bytes need %d point bytes, got %d" % (sc.size, n * enc_size(group, ENC_UNCOMPRESSED),
+                                                                                pts.size))
         out = np.empty(enc_size(group, ENC_UNCOMPRESSED), dtype=np.uint8)
         fn = self.lib.p2b_g2_msm if group == G2 else self.lib.p2b_g1_msm
         self._check(fn(self.h, _ptr(pts), _ptr(sc), n, _ptr(out)))

@@ -143,31 +143,57 @@ class MPCParameters:
         cs_hash = hashlib.blake2b(body).digest()                                     # HashWriter over params.write (:365-375)
         return cls(body + cs_hash + struct.pack(">I", 0))
 
-    def __init__(self, data):
+    def __init__(self, data, validated=False):
         self.data = np.array(np.frombuffer(bytes(data), dtype=np.uint8)) if not isinstance(data, np.ndarray) else data
+        # True once every point went through the checked codec (read(checked=True)): the MSM kernels decode unchecked, so
+        # verify_contribution re-validates H / L of an object that was constructed from raw bytes
+        self.validated = bool(validated)
 
     @classmethod
     def read(cls, reader, disallow_points_at_infinity=False, checked=True, ctx=None):
-        """MPCParameters::read (phase2/src/parameters.rs:682-703 -> Parameters::read, groth16/mod.rs:287-383): every point
-        is range-checked, `checked` adds is_on_curve, `disallow_points_at_infinity` rejects infinity -- done section by
-        section with the GPU bulk codec.  Raises IOError("InvalidData ...") like the reference's io::Error."""
+        """MPCParameters::read (phase2/src/parameters.rs:682-703 -> Parameters::read, groth16/mod.rs:287-383).
+        As in the reference the caller's flags only govern h, l, a, b_g1, b_g2 (`read_g1` / `read_g2`, mod.rs:295-327).
+        The verifying key is always curve-checked (`into_affine()`, mod.rs:160-185) and its `ic` always rejects infinity
+        (mod.rs:188-199); every stored contribution's delta_after, s, s_delta (G1) and r_delta (G2) is always curve-checked
+        and must not be infinity (PublicKey::read, phase2/src/keypair.rs:64-100).  All of it runs section by section on
+        the GPU bulk codec.  Raises IOError("InvalidData ...") like the reference's io::Error."""
         buf = reader if isinstance(reader, (bytes, bytearray, memoryview, np.ndarray)) else reader.read()
         self = cls(buf)
         ctx = ctx or _lib.Context(0)
-        flags = (_lib.CHECK_INPUT if checked else 0) | (_lib.REJECT_INFINITY if disallow_points_at_infinity else 0)
+        caller = (_lib.CHECK_INPUT if checked else 0) | (_lib.REJECT_INFINITY if disallow_points_at_infinity else 0)
         lay = params_layout(self.data)
-        for name, (off, n, size, group) in lay.items():
-            if group is None or n == 0:
-                continue
+
+        def validate(name, group, points, flags, index_of=lambda i: i):
+            if points.size == 0:
+                return
             try:
-                ctx.recode(group, self.data[off: off + n * size], _lib.ENC_UNCOMPRESSED, _lib.ENC_UNCOMPRESSED, flags)
+                ctx.recode(group, points, _lib.ENC_UNCOMPRESSED, _lib.ENC_UNCOMPRESSED, flags)
             except _lib.P2BError as e:
                 if e.code in (_lib.EDECODE, _lib.EINFINITY_IN):
                     what = "point at infinity" if e.code == _lib.EINFINITY_IN else \
                         {1: "NotOnCurve", 2: "CoordinateDecodingError", 3: "UnexpectedInformation",
                          4: "UnexpectedCompressionMode"}.get(e.sub, "decoding error")
-                    raise IOError("InvalidData: %s in %s[%d]" % (what, name, e.index))
+                    raise IOError("InvalidData: %s in %s[%d]" % (what, name, index_of(e.index)))
                 raise
+
+        for name, (off, n, size, group) in lay.items():
+            if group is None or n == 0:
+                continue
+            if name in ("alpha_g1", "beta_g1", "beta_g2", "gamma_g2", "delta_g1", "delta_g2"):
+                flags = _lib.CHECK_INPUT
+            elif name == "ic":
+                flags = _lib.CHECK_INPUT | _lib.REJECT_INFINITY
+            else:
+                flags = caller
+            validate(name, group, self.data[off: off + n * size], flags)
+        off, n, _, _ = lay["contributions"]
+        if n:
+            pk = self.data[off: off + n * 384].reshape(n, 384)
+            strict = _lib.CHECK_INPUT | _lib.REJECT_INFINITY
+            validate("contributions(delta_after, s, s_delta)", 0, np.ascontiguousarray(pk[:, :192]).reshape(-1), strict,
+                     lambda i: i // 3)
+            validate("contributions(r_delta)", 1, np.ascontiguousarray(pk[:, 192:320]).reshape(-1), strict)
+        self.validated = bool(checked)
         return self
 
     def write(self, writer):
@@ -204,8 +230,8 @@ class VerificationError(Exception):
 def merge_pairs(ctx, v1, v2, rng=None, scalar_bits=253):
     """Random linear combination (sum rho_i v1_i, sum rho_i v2_i) over G1 vectors (phase2/src/utils.rs:59-105): two MSMs.
     `scalar_bits`: see powersoftau._random_scalars (253 = full-size scalars like the reference's Fr::rand)."""
-    from .powersoftau import _random_scalars
-    rng = rng or np.random.default_rng()
+    from .powersoftau import _random_scalars, system_rng
+    rng = rng or system_rng()
     n = v1.size // 64
     if n != v2.size // 64:
         raise ValueError("merge_pairs: length mismatch")
@@ -260,9 +286,17 @@ def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253, merg
         from .powersoftau import G2_ONE
         if not _lib.same_ratio((g1_one, delta_after), (G2_ONE, d2a)):
             fail("delta_g2 is inconsistent with delta_g1")
-        if merge is None:
+        if merge is None or not (getattr(before, "validated", False) and getattr(after, "validated", False)):
             ctx = ctx or _lib.Context(0)                                            # only the H / L checks need the GPU
+        if merge is None:
             merge = lambda a, b: merge_pairs(ctx, a, b, rng, scalar_bits)
+        # The MSM decodes its points unchecked.  The reference can only get here through MPCParameters::read(checked = true)
+        # (verify.rs); objects built from raw bytes are put through the checked codec first (curve membership of H / L).
+        for m, lay in ((before, lb), (after, la)):
+            if not getattr(m, "validated", False):
+                for name in ("h", "l"):
+                    if lay[name][1]:
+                        ctx.recode(0, raw(m, lay, name), _lib.ENC_UNCOMPRESSED, _lib.ENC_UNCOMPRESSED, _lib.CHECK_INPUT)
         for name in ("h", "l"):                                                     # updated with delta^-1: ratios reversed
             if not _lib.same_ratio(merge(raw(before, lb, name), raw(after, la, name)), (d2a, d2b)):
                 fail("%s query was not multiplied by delta^-1" % name)

@@ -287,13 +287,27 @@ def _read_points(ctx, amap, parameters, compressed, checked, name, start, count)
         BatchedAccumulator._raise(e)
 
 
+class system_rng:
+    """Coefficients for the verifier's random linear combinations from the operating system's CSPRNG (`os.urandom`) -- the
+    counterpart of the reference's `thread_rng()` (powersoftau/src/utils.rs:118-124, phase2/src/utils.rs:76-78).  An
+    adversarial contributor must not be able to predict them, so a seedable statistical generator is not a valid default;
+    tests and benches may still pass any object with a `bytes(n)` method (e.g. numpy's Generator) for reproducibility."""
+
+    @staticmethod
+    def bytes(n):
+        return os.urandom(n)
+
+
+MIN_SCALAR_BITS = 128
+
+
 def _random_scalars(rng, n, bits=253):
     """n random scalars below 2^bits (32 bytes big-endian each).  The reference draws full-size Fr::rand from thread_rng
     (utils.rs:118-124); 253 bits (< r) is the faithful default.  bits=128 is an opt-in for big verifications: the soundness
     error of the random linear combination is 2^-128 instead of 2^-253, the zero top digits never reach a bucket (the MSM
-    does about half the work) and half the random bytes are drawn."""
-    if not 8 <= bits <= 253 or bits % 8 not in (0, 5):
-        raise ValueError("bits must be a multiple of 8, or 253")
+    does about half the work) and half the random bytes are drawn.  Fewer than 128 bits are refused."""
+    if not MIN_SCALAR_BITS <= bits <= 253 or bits % 8 not in (0, 5):
+        raise ValueError("scalar_bits must be a multiple of 8 in [%d, 248], or 253" % MIN_SCALAR_BITS)
     nbytes = (bits + 7) // 8
     a = np.zeros((n, 32), dtype=np.uint8)
     a[:, 32 - nbytes:] = np.frombuffer(rng.bytes(nbytes * n), dtype=np.uint8).reshape(n, nbytes)
@@ -311,7 +325,8 @@ def verify_transformation(input_map, output_map, key, digest, input_is_compresse
     Returns True / False like the reference; a chunk that does not deserialize raises (the reference panics).
     `scalar_bits`: size of the random coefficients (see _random_scalars; 253 = the reference's full-size scalars)."""
     ctx = ctx or BatchedAccumulator.context()
-    rng = rng or np.random.default_rng()
+    rng = rng or system_rng()
+    _random_scalars(rng, 0, scalar_bits)                # refuse a too-small scalar_bits before any work
     assert len(digest) == 64
     p = parameters
     # The per-chunk same_ratio checks (two pairings each, ~35 ms on one core) run on host threads while the GPU works on
@@ -382,9 +397,10 @@ def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, i
         if end == start:
             raise RuntimeError("Chunk does not have a min and max")            # the reference's panic (:462)
         size = end - start + 1 + (0 if end == p.powers_length - 1 else 1)      # one extra element: chunks overlap
-        if check_input_for_correctness:
-            for name in ("tau_g1", "tau_g2", "alpha_g1", "beta_g1"):
-                before(name, start, size)
+        # the reference always deserializes the challenge chunk (read_chunk, :404-410): even with CheckForCorrectness::No a
+        # bad flag, a non-canonical coordinate or a point at infinity in `before` panics
+        for name in ("tau_g1", "tau_g2", "alpha_g1", "beta_g1"):
+            before(name, start, size)
         v = after("tau_g1", start, size)
         if not powers_ok(0, v, g2_pair):
             return False
@@ -401,8 +417,7 @@ def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, i
         if end == start:
             raise RuntimeError("Chunk does not have a min and max")            # (:526)
         size = end - start + 1 + (0 if end == p.powers_g1_length - 1 else 1)
-        if check_input_for_correctness:
-            before("tau_g1", start, size)
+        before("tau_g1", start, size)
         v = after("tau_g1", start, size)
         if not powers_ok(0, v, g2_pair):
             return False

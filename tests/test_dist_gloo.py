@@ -16,10 +16,24 @@ class OracleCtx:
         self.oc = oc
 
     def msm(self, group, points, scalars):
-        return self.oc.msm(group, bytes(points), bytes(scalars), threads=2)
+        from phase2_bn254_b200 import lib
+        try:
+            return self.oc.msm(group, bytes(points), bytes(scalars), threads=2)
+        except self.oc.OracleError as e:
+            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
 
     def sum_points(self, group, points):
         return self.oc.sum_points(group, bytes(points))
+
+    def recode(self, group, points, in_enc, out_enc, flags=0, out=None):
+        from phase2_bn254_b200 import lib
+        import numpy as np
+        try:
+            res = self.oc.batch_mul(group, bytes(np.asarray(points)), (1).to_bytes(32, "big"), in_enc, out_enc,
+                                    bool(flags & lib.CHECK_INPUT), bool(flags & lib.REJECT_INFINITY), threads=2)
+        except self.oc.OracleError as e:
+            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
+        return np.frombuffer(res, dtype=np.uint8)
 
 
 def _worker(rank, world, port, q):
@@ -87,7 +101,18 @@ def _verify_worker(rank, world, port, q):
             rejected = False
         except VerificationError:
             rejected = True
-        q.put((rank, got == expected, rejected))
+        # a point that does not decode in ONE rank's shard: that rank must still join the all-gather (no deadlock) and
+        # every rank must raise (same verdict everywhere)
+        hoff, hn = lay["h"][0], lay["h"][1]
+        v1 = np.array(before.data[hoff: hoff + 64 * hn])
+        v2 = np.array(np.frombuffer(after, dtype=np.uint8)[hoff: hoff + 64 * hn])
+        v2[64 * (hn - 1)] |= 0x80                                            # flag bit in an uncompressed point: last rank's slice
+        try:
+            pdist.sharded_merge_pairs(ctx, v1, v2, rank, world, rng=np.random.default_rng(30 + rank))
+            raised = False
+        except lib.P2BError:
+            raised = True
+        q.put((rank, got == expected, rejected and raised))
     finally:
         dist.destroy_process_group()
 

@@ -223,3 +223,69 @@ def test_mpc_parameters_new_host_logic(lib, oracle):
         MPCParameters.new(loose, False, lambda exp: radix, ctx=ctx)
     with pytest.raises(IOError):
         MPCParameters.new(circuit, False, lambda exp: radix[:-1], ctx=ctx)
+
+
+def test_mpc_parameters_read_is_as_strict_as_the_reference(lib, oracle):
+    """MPCParameters::read: the verifying key and the stored contributions are validated whatever the caller's flags say
+    (VerifyingKey::read groth16/mod.rs:160-199 always uses into_affine() and rejects infinity in ic; PublicKey::read
+    phase2/src/keypair.rs:64-100 rejects infinity and off-curve points); only h, l, a, b_g1, b_g2 follow `checked` /
+    `disallow_points_at_infinity`."""
+    from phase2_bn254_b200.phase2 import MPCParameters, params_layout
+    ctx = OracleCtx(oracle)
+    _, after, _, _ = contribution_by_hand(lib, 4)
+    lay = params_layout(after)
+    assert MPCParameters.read(after, ctx=ctx).validated
+    assert not MPCParameters.read(after, checked=False, ctx=ctx).validated
+    inf1, inf2 = bytes([0x40]) + bytes(63), bytes([0x40]) + bytes(127)
+
+    def tampered(off, repl):
+        b = bytearray(after)
+        b[off: off + len(repl)] = repl
+        return bytes(b)
+
+    off_curve = bytearray(after[lay["alpha_g1"][0]: lay["alpha_g1"][0] + 64])
+    off_curve[63] ^= 1
+    cases = [("alpha_g1 off curve", tampered(lay["alpha_g1"][0], bytes(off_curve))),
+             ("ic infinity", tampered(lay["ic"][0] + 64, inf1)),
+             ("contribution s infinity", tampered(lay["contributions"][0] + 64, inf1)),
+             ("contribution s_delta off curve", tampered(lay["contributions"][0] + 128, bytes(off_curve))),
+             ("contribution r_delta infinity", tampered(lay["contributions"][0] + 192, inf2))]
+    for what, buf in cases:
+        for checked in (False, True):
+            with pytest.raises(IOError):
+                MPCParameters.read(buf, disallow_points_at_infinity=False, checked=checked, ctx=ctx)
+    # the caller's flags govern the query vectors: infinity in h is tolerated unless disallowed, off-curve only seen when checked
+    h_inf = tampered(lay["h"][0], inf1)
+    MPCParameters.read(h_inf, ctx=ctx)
+    with pytest.raises(IOError):
+        MPCParameters.read(h_inf, disallow_points_at_infinity=True, ctx=ctx)
+    h_off = tampered(lay["h"][0], bytes(off_curve))
+    MPCParameters.read(h_off, checked=False, ctx=ctx)
+    with pytest.raises(IOError):
+        MPCParameters.read(h_off, checked=True, ctx=ctx)
+    # vk infinity is not rejected by VerifyingKey::read for the single elements (only ic)
+    MPCParameters.read(tampered(lay["gamma_g2"][0], inf2), ctx=ctx)
+
+
+def test_verify_contribution_revalidates_unchecked_parameters(lib, oracle):
+    """The MSM decodes unchecked; an MPCParameters built from raw bytes (no read(checked=True)) has its H / L put through the
+    checked codec by verify_contribution, so an off-curve element is a VerificationError, not a silently wrong sum."""
+    from phase2_bn254_b200.phase2 import MPCParameters, VerificationError, verify_contribution
+    ctx = OracleCtx(oracle)
+    before, after, expected, lay = contribution_by_hand(lib, 4)
+    assert verify_contribution(before, MPCParameters(after), ctx=ctx, rng=np.random.default_rng(1)) == expected
+    bad = bytearray(after)
+    bad[lay["l"][0] + 64 + 63] ^= 1
+    with pytest.raises(VerificationError):
+        verify_contribution(before, MPCParameters(bytes(bad)), ctx=ctx, rng=np.random.default_rng(1))
+
+
+def test_scalar_bits_floor_and_system_rng():
+    from phase2_bn254_b200.powersoftau import _random_scalars, system_rng
+    for bits in (8, 64, 120):
+        with pytest.raises(ValueError):
+            _random_scalars(system_rng(), 4, bits)
+    a, b = _random_scalars(system_rng(), 64, 128), _random_scalars(system_rng(), 64, 128)
+    assert a.size == 64 * 32 and not np.array_equal(a, b)
+    assert not a.reshape(64, 32)[:, :16].any() and a.reshape(64, 32)[:, 16:].any()
+    assert (_random_scalars(system_rng(), 64, 253).reshape(64, 32)[:, 0] < 0x20).all()
