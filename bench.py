@@ -51,47 +51,72 @@ def host_cores():
 
 
 # ----------------------------------------------------------------------------------------------- CPU legs (oracle)
+def bellman_windows(n):
+    """bellman's window rule (bellman/src/multiexp.rs:341-345): c = 3 if n < 32 else ceil(ln n); windows while skip < 254."""
+    import math
+    c = 3 if n < 32 else int(math.ceil(math.log(n)))
+    return c, (254 + c - 1) // c
+
+
 def cpu_points_scalars(n, seed=1):
-    """n G1 points tau^(i+1) G and n scalars, generated on the CPU with the oracle (bounded sample sizes only)."""
+    """n G1 points and n uniform scalars for the CPU arm.  Above 2^16 terms the 2^16 distinct points tau^(i+1) G are tiled:
+    Pippenger's cost per term does not depend on the point values (every term is one mixed add into a bucket chosen by the
+    scalar), and generating 2^26 distinct points with the CPU restatement's batch_exp would take minutes."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import oracle as oc
-    pts = oc.batch_mul_powers(0, G1_GEN * n, be(TAU), None, 1, threads=host_cores())
+    distinct = min(n, 1 << 16)
+    base = np.frombuffer(oc.batch_mul_powers(0, G1_GEN * distinct, be(TAU), None, 1, threads=host_cores()), dtype=np.uint8)
+    pts = np.tile(base, n // distinct) if n > distinct else base
     rng = np.random.default_rng(seed)
-    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc = np.empty((n, 32), dtype=np.uint8)
+    step = 1 << 22
+    for lo in range(0, n, step):
+        sc[lo:lo + step] = rng.integers(0, 256, size=(min(step, n - lo), 32), dtype=np.uint8)
     sc[:, 0] &= 0x1f
-    return pts, sc.tobytes()
+    return pts, sc.reshape(-1)
 
 
-def cpu_msm_rate(log_sample, steps=1, warmup=0):
-    """(Mscalar-mul/s, seconds per MSM, cores) of the oracle's Pippenger (bellman's algorithm) on 2^log_sample terms."""
-    n = 1 << log_sample
-    pts, sc = cpu_points_scalars(n)
+def cpu_msm(pts, sc, cores):
+    """One oracle Pippenger over host arrays: (result bytes, decode seconds, Pippenger seconds)."""
     import oracle as oc
-    cores = host_cores()
-    for _ in range(warmup):
-        oc.msm(0, pts, sc, threads=cores)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        oc.msm(0, pts, sc, threads=cores)
-    dt = (time.perf_counter() - t0) / steps
-    return n / dt / 1e6, dt, cores
+    return oc.msm_timed(0, pts, sc, threads=cores)
 
 
 def run_reference(args, rank):
+    """The CPU arm: the oracle's restatement of bellman's multiexp (the reference itself is Rust and cannot be built here) on
+    the SAME config as the GPU arm -- 2^log_n terms per step, bellman's own window width for that size -- on all host
+    threads.  A step is one full-size MSM (about a minute at 2^26 on 16 cores), so the number of steps actually run is
+    bounded by a time budget and reported; the timed figure is the Pippenger proper (the wire decode of the inputs, which
+    the reference's multiexp does not do, is reported separately)."""
     if rank != 0:
         return
-    log_sample = args.ref_log_n
-    rate, dt, cores = cpu_msm_rate(log_sample, steps=args.steps, warmup=min(args.warmup, 1))
+    log_n = args.ref_log_n if args.ref_log_n else args.log_n
+    n = 1 << log_n
+    cores = host_cores()
+    pts, sc = cpu_points_scalars(n)
+    c, nwin = bellman_windows(n)
+    budget_s, t_start, times, dec = args.ref_budget_s, time.perf_counter(), [], 0.0
+    while len(times) < max(1, args.steps):
+        _, d, t = cpu_msm(pts, sc, cores)
+        times.append(t)
+        dec = d
+        if time.perf_counter() - t_start + t > budget_s:
+            break
+    dt = sum(times) / len(times)
+    rate = n / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "g1_msm_2^%d" % args.log_n, "terms_per_gpu": 1 << args.log_n},
+        "steps": len(times), "warmup": 0, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "g1_msm_2^%d" % log_n, "terms_per_gpu": n, "window_bits": c, "windows": nwin,
+                   "steps_requested": args.steps, "time_budget_s": budget_s},
         "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "one Pippenger MSM over 2^%d of the workload's terms per step (bellman window rule "
-                                   "c=ceil(ln n), one task per window and chunk on all host threads); the reference is Rust "
-                                   "and cannot be built here, this is oracle/p2b_oracle.c" % log_sample},
+                         "sample": "%d full Pippenger MSM(s) over 2^%d terms (bellman window rule c = ceil(ln n) = %d, %d windows, "
+                                   "one task per window and point chunk on all %d host threads); Pippenger proper timed, wire "
+                                   "decode of the inputs (%.1f s, not part of the reference's multiexp) excluded; the reference is "
+                                   "Rust and cannot be built here, this is oracle/p2b_oracle.c; 2^16 distinct points tiled"
+                                   % (len(times), log_n, c, nwin, cores, dec)},
         "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -180,6 +205,38 @@ def make_points(torch, np, ctx, group, n, start, device):
     ctx.sync()
     del src
     return pts
+
+
+def pageable_msm(args, torch, np, ctx, np_pts, np_sc, m):
+    """e2e MSM over m terms read from memory maps of real files (pageable: staged through the library's pinned rings by
+    host threads, csrc/hostio.cu) next to the same call on page-locked buffers."""
+    import tempfile
+    out = {}
+    d = tempfile.mkdtemp(prefix="p2b_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") and args.mmap_dir is None else args.mmap_dir)
+    try:
+        fp, fs = os.path.join(d, "points"), os.path.join(d, "scalars")
+        np_pts[: 64 * m].tofile(fp)
+        np_sc[: 32 * m].tofile(fs)
+        pm, sm = np.memmap(fp, dtype=np.uint8, mode="r"), np.memmap(fs, dtype=np.uint8, mode="r")
+        res = {}
+        for name, a, b in (("pinned", np_pts[: 64 * m], np_sc[: 32 * m]), ("mmap", pm, sm)):
+            ctx.msm(0, a, b)
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                res[name] = ctx.msm(0, a, b)
+                ts.append(time.perf_counter() - t0)
+            out[name + "_ms"] = round(min(ts) * 1e3, 3)
+        out["terms"] = m
+        out["mmap_over_pinned"] = round(out["mmap_ms"] / out["pinned_ms"], 3)
+        out["same_result"] = res["pinned"] == res["mmap"]
+        out["files_in"] = d.rsplit("/", 1)[0]
+        del pm, sm
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+    return out
 
 
 def timed(torch, stream, fn, reps):
@@ -286,6 +343,25 @@ def run_ours(args, rank, world, local_rank):
         e2e_ms = float(t.item())
     e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
     assert result["e"] == result["r"], "host-buffer and device-buffer MSM disagree"
+    # ---- the CPU restatement on the GPU arm's OWN inputs, full size (rank 0, one GPU): the parity check at the size the
+    #      metric is quoted on, and the cpu_baseline of this line
+    cpu_line = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        cores = host_cores()
+        cres, cdec, cdt = cpu_msm(np_pts, np_sc, cores)
+        c_bits, c_win = bellman_windows(n)
+        cpu_line = {"value": round(n / cdt / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "ONE full Pippenger MSM over the GPU arm's own 2^%d points and scalars (%.1f s; bellman window rule "
+                              "c = %d, %d windows; wire decode of the inputs, %.1f s, excluded), oracle/p2b_oracle.c = C restatement "
+                              "of bellman multiexp on all host threads" % (args.log_n, cdt, c_bits, c_win, cdec),
+                    "result_matches_gpu": cres == result["r"]}
+        assert cres == result["r"], "GPU MSM at 2^%d differs from the oracle" % args.log_n
+    # ---- pageable caller buffers (memory maps of real files, as the reference's binaries pass them): MSM 2^24 from an
+    #      np.memmap next to the same call on the pinned copy
+    pageable = None
+    if world == 1 and rank == 0 and not args.no_extras:
+        pageable = pageable_msm(args, torch, np, ctx, np_pts, np_sc, min(n, 1 << 24))
     del h_pts, h_sc, np_pts, np_sc
 
     if rank != 0:
@@ -335,6 +411,8 @@ def run_ours(args, rank, world, local_rank):
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
         "result_x": result["r"][:32].hex(),
     }
+    if pageable:
+        line["e2e"]["pageable_caller_buffers_msm_2^%d" % (pageable["terms"].bit_length() - 1)] = pageable
     clocks.stop()
 
     if world == 1:
@@ -352,10 +430,9 @@ def run_ours(args, rank, world, local_rank):
                 exp = oc.pot_transform(chb, 10, 256, be(key.tau), be(key.alpha), be(key.beta), threads=1)
                 line["extras"]["pot_transform_2^10"].update({"cpu_1thread_s": round(time.perf_counter() - t0, 3),
                                                              "response_matches_oracle": exp[64:] == body})
-            rate, dt, cores = cpu_msm_rate(args.ref_log_n)
-            line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "one Pippenger MSM over 2^%d of the workload's terms (%.1f s), oracle/p2b_oracle.c "
-                                              "= C restatement of bellman multiexp on all host threads" % (args.ref_log_n, dt)}
+            cores = host_cores()
+            line["cpu_baseline"] = cpu_line
+            line["msm_2^%d_matches_oracle" % args.log_n] = bool(cpu_line and cpu_line["result_matches_gpu"])
             if "extras" in line:    # the CPU restatement of the other paths, bounded samples, same host cores
                 import numpy as np
                 import oracle as oc
@@ -502,6 +579,27 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
         if size == 10:
             out["_pot10"] = (chn.tobytes(), key, rsn[64:end].tobytes())
         if size == 20:
+            # the same call the way compute_constrained makes it: memory maps of the challenge and response FILES (pageable)
+            import shutil
+            import tempfile
+            d = tempfile.mkdtemp(prefix="p2b_bench_", dir=args.mmap_dir or ("/dev/shm" if os.path.isdir("/dev/shm") else None))
+            try:
+                chn.tofile(os.path.join(d, "challenge"))
+                with open(os.path.join(d, "response"), "wb") as f:
+                    f.truncate(prm.contribution_size)
+                cm = np.memmap(os.path.join(d, "challenge"), dtype=np.uint8, mode="r")
+                rm = np.memmap(os.path.join(d, "response"), dtype=np.uint8, mode="r+")
+                tm = []
+                for _ in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    BatchedAccumulator.transform(cm, rm, False, True, False, key, prm, ctx=ctx)
+                    tm.append(time.perf_counter() - t0)
+                out["pot_transform_2^20"].update({"mmap_files_wall_s": round(min(tm), 4),
+                                                  "mmap_same_bytes": bool(np.array_equal(rm[64:end], rsn[64:end]))})
+                del cm, rm
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
             # -- next row: verify_transformation of that response (compressed) against the challenge: per chunk
             #    of 2^18 powers eight Pippenger MSMs on the GPU (power_pairs over tau_g1, tau_g2, alpha_g1, beta_g1), the
             #    same_ratio pairings on host threads
@@ -550,8 +648,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=26, help="log2 of the MSM terms per GPU")
-    ap.add_argument("--ref-log-n", type=int, default=20, help="log2 of the bounded CPU sample")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="--impl reference: log2 of the terms (default: --log-n, the same config)")
+    ap.add_argument("--ref-budget-s", type=float, default=120.0, help="--impl reference: stop starting new full-size steps after this long")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--mmap-dir", default=None, help="directory for the memory-mapped input files of the pageable-buffer extras")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

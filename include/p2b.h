@@ -89,6 +89,10 @@ enum {
     P2B_PROF_FFT_PASS = 5,       /* radix-256 FFT passes */
     P2B_PROF_SLOTS = 6
 };
+/* Caller buffers may be pageable (the reference's callers pass memory maps of the challenge / response files,
+ * powersoftau/src/bin/compute_constrained.rs:83-132): such buffers are staged through pinned rings by host threads
+ * (csrc/hostio.cu); page-locked buffers are copied directly.  Bytes that took the staged path so far: */
+void p2b_io_stats(p2b_ctx *ctx, uint64_t *staged_h2d_bytes, uint64_t *staged_d2h_bytes);
 int p2b_profile_enable(p2b_ctx *ctx, int on);
 int p2b_profile_read(p2b_ctx *ctx, int slot, double *total_ms, uint64_t *kernels);
 

@@ -137,6 +137,18 @@ def msm(group, points, scalars, threads=1):
     return bytes(out)
 
 
+def msm_timed(group, points, scalars, threads=1):
+    """msm() plus (wire-decode seconds, Pippenger seconds): the reference's multiexp takes decoded G1Affine / FrRepr values,
+    so only the second figure is comparable with it."""
+    n = len(scalars) // 32
+    out = (ctypes.c_uint8 * point_size(group, UNCOMPRESSED))()
+    sec = (ctypes.c_double * 2)()
+    rc = lib().orc_msm_timed(group, _cin(points), _cin(scalars), ctypes.c_size_t(n), out, threads, sec)
+    if rc:
+        raise OracleError(rc)
+    return bytes(out), sec[0], sec[1]
+
+
 def sum_points(group, points):
     n = len(points) // point_size(group, UNCOMPRESSED)
     out = (ctypes.c_uint8 * point_size(group, UNCOMPRESSED))()

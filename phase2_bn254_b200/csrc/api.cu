@@ -63,6 +63,10 @@ int ctx_collect_error(Ctx *c) {
     P2B_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     P2B_CUDA(c, cudaStreamSynchronize(c->stream));
     P2B_CUDA(c, cudaStreamSynchronize(c->copy_out));
+    {
+        int rc = io_flush(c);
+        if (rc) return rc;
+    }
     unsigned long long e = *c->h_err;
     if (e == ERR_NONE) return P2B_OK;
     cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream);   // a reported error never leaks into later calls
@@ -111,11 +115,11 @@ static int run_host_job(Ctx *c, const HostJob &j) {
         if (ci >= 2) P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, ev_cdone[b], 0));
         else P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, c->ev[6], 0));   // after earlier work on the compute stream
         char *d_in = (char *)c->stage_in[b].p;
-        P2B_CUDA(c, cudaMemcpyAsync(d_in, j.in + off * isz, m * isz, cudaMemcpyHostToDevice, c->copy_in));
+        if ((rc = io_h2d(c, d_in, j.in + off * isz, m * isz, c->copy_in))) return rc;
         ScalarSpec sc = j.sc;
         if (sc.mode == 0) {
             char *d_sc = d_in + chunk * isz;
-            P2B_CUDA(c, cudaMemcpyAsync(d_sc, j.host_scalars + off * 32, m * 32, cudaMemcpyHostToDevice, c->copy_in));
+            if ((rc = io_h2d(c, d_sc, j.host_scalars + off * 32, m * 32, c->copy_in))) return rc;
             sc.d_scalars = d_sc;
         } else if (sc.mode == 2) sc.start = j.sc.start + off;
         P2B_CUDA(c, cudaEventRecord(ev_in[b], c->copy_in));
@@ -126,7 +130,7 @@ static int run_host_job(Ctx *c, const HostJob &j) {
         P2B_CUDA(c, cudaEventRecord(ev_cdone[b], c->stream));
         // D2H
         P2B_CUDA(c, cudaStreamWaitEvent(c->copy_out, ev_cdone[b], 0));
-        P2B_CUDA(c, cudaMemcpyAsync(j.out + off * osz, c->stage_out[b].p, m * osz, cudaMemcpyDeviceToHost, c->copy_out));
+        if ((rc = io_d2h(c, j.out + off * osz, c->stage_out[b].p, m * osz, c->copy_out))) return rc;
         P2B_CUDA(c, cudaEventRecord(ev_odone[b], c->copy_out));
     }
     // the next job may reuse both staging pairs: make the compute stream wait for the last two D2H copies,
@@ -497,6 +501,7 @@ void p2b_destroy(p2b_ctx *h) {
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    io_destroy(c);
     DevBuf *bufs[] = {&c->jac, &c->prefix, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1], &c->scal,
                       &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->fft_tw, &c->gtable, &c->gfft};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -521,6 +526,10 @@ void p2b_error_detail(p2b_ctx *h, uint64_t *index, int *sub) {
 }
 void *p2b_stream(p2b_ctx *h) { return h ? (void *)h->c.stream : nullptr; }
 uint64_t p2b_launch_count(p2b_ctx *h) { return h ? h->c.launches : 0; }
+
+void p2b_io_stats(p2b_ctx *h, uint64_t *staged_in, uint64_t *staged_out) {
+    if (h) io_stats(&h->c, staged_in, staged_out);
+}
 
 int p2b_profile_enable(p2b_ctx *h, int on) {
     if (!h) return P2B_EARG;

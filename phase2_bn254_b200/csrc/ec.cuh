@@ -45,6 +45,7 @@ P2B_HD Fq2 sqr(const Fq2 &a) {
     r.c1 = dbl(ab);
     return r;
 }
+P2B_HD Fq2 sqr_ded(const Fq2 &a) { return sqr(a); }
 P2B_HD Fq2 mul_fq(const Fq2 &a, const Fq &b) { Fq2 r; r.c0 = mul(a.c0, b); r.c1 = mul(a.c1, b); return r; }
 P2B_HD Fq2 inv(const Fq2 &a) {  // fq2.rs:182-199
     Fq t = inv(add(sqr(a.c0), sqr(a.c1)));

@@ -423,10 +423,10 @@ static int fft_host(Ctx *c, uint8_t *data, uint32_t log_n, int inverse, int cose
     const size_t bytes = (size_t)32 << log_n;
     if ((rc = dev_reserve(c, c->stage_in[0], bytes))) return rc;
     if ((rc = dev_reserve(c, c->misc, bytes))) return rc;
-    P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[0].p, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = io_h2d(c, c->stage_in[0].p, data, bytes, c->stream))) return rc;
     void *res = nullptr;
     if ((rc = fft_run(c, c->stage_in[0].p, c->misc.p, log_n, inverse, coset, &res))) return rc;
-    P2B_CUDA(c, cudaMemcpyAsync(data, res, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = io_d2h(c, data, res, bytes, c->stream))) return rc;
     return ctx_collect_error(c);
 }
 static int fft_dev(Ctx *c, void *d_data, uint32_t log_n, int inverse, int coset) {

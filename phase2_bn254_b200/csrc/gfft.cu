@@ -210,10 +210,10 @@ template <class F> static int group_fft_host(Ctx *c, int g2, const uint8_t *in, 
     if ((rc = dev_reserve(c, c->stage_out[0], d * osz))) return rc;
     GfftArea<F> a;
     a.carve(c->gfft.p, d);
-    P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[0].p, in, d * isz, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = io_h2d(c, c->stage_in[0].p, in, d * isz, c->stream))) return rc;
     if ((rc = to_raw(c, g2, c->stage_in[0].p, a.X, d, in_enc, flags, 0))) return rc;
     if ((rc = group_fft_dev<F>(c, a, log_d, inverse, g2, c->stage_out[0].p, out_enc, flags))) return rc;
-    P2B_CUDA(c, cudaMemcpyAsync(out, c->stage_out[0].p, d * osz, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = io_d2h(c, out, c->stage_out[0].p, d * osz, c->stream))) return rc;
     return ctx_collect_error(c);
 }
 
@@ -265,7 +265,7 @@ static int prepare_phase2(Ctx *c, const uint8_t *acc, uint64_t acc_len, uint32_t
     const struct { int g2; uint64_t off; } vecs[4] = {{0, off_tau_g1}, {1, off_tau_g2}, {0, off_alpha}, {0, off_beta}};
     for (int v = 0; v < 4; v++) {
         const uint64_t isz = vecs[v].g2 ? g2s : g1, osz = vecs[v].g2 ? 128 : 64;
-        P2B_CUDA(c, cudaMemcpyAsync(stg, acc + vecs[v].off, d * isz, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = io_h2d(c, stg, acc + vecs[v].off, d * isz, c->stream))) return rc;
         if (vecs[v].g2) {
             GfftArea<Fq2> a;
             a.carve(c->gfft.p, d);
@@ -285,13 +285,13 @@ static int prepare_phase2(Ctx *c, const uint8_t *acc, uint64_t acc_len, uint32_t
         const uint64_t np = 2 * d - 1;
         GfftArea<Fq> a;
         a.carve(c->gfft.p, 2 * d);
-        P2B_CUDA(c, cudaMemcpyAsync(stg, acc + off_tau_g1, np * g1, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = io_h2d(c, stg, acc + off_tau_g1, np * g1, c->stream))) return rc;
         if ((rc = to_raw(c, 0, stg, a.X, np, enc, dflags, 0))) return rc;
         k_gdiff<Fq><<<grid_for(c, d - 1), 128, 0, c->stream>>>(a.X, a.jx, a.jy, a.jz, d, d - 1);
         c->launches++;
         if ((rc = normalize_to<Fq>(c, a.jx, a.jy, a.jz, a.prefix, img + o, d - 1, ENC_UNCOMPRESSED))) return rc;
     }
-    P2B_CUDA(c, cudaMemcpyAsync(out, img, radix_file_size(m), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = io_d2h(c, out, img, radix_file_size(m), c->stream))) return rc;
     return ctx_collect_error(c);
 }
 

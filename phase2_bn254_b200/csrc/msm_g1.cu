@@ -53,8 +53,8 @@ static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_
         if (m > n - off) m = n - off;
         P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, ci >= 2 ? ev_done[b] : c->ev[6], 0));
         char *d_pts = (char *)c->stage_in[b].p, *d_sc = d_pts + chunk * psz;
-        P2B_CUDA(c, cudaMemcpyAsync(d_pts, points + off * psz, m * psz, cudaMemcpyHostToDevice, c->copy_in));
-        P2B_CUDA(c, cudaMemcpyAsync(d_sc, scalars + off * 32, m * 32, cudaMemcpyHostToDevice, c->copy_in));
+        if ((rc = io_h2d(c, d_pts, points + off * psz, m * psz, c->copy_in))) return rc;
+        if ((rc = io_h2d(c, d_sc, scalars + off * 32, m * 32, c->copy_in))) return rc;
         P2B_CUDA(c, cudaEventRecord(ev_in[b], c->copy_in));
         P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
         const int phase = (ci == 0 ? MSM_FIRST : 0) | (off + m == n ? MSM_LAST : 0);
@@ -76,8 +76,8 @@ static int msm_host(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalar
     if ((rc = dev_reserve(c, c->stage_in[0], (n ? n : 1) * psz))) return rc;
     if ((rc = dev_reserve(c, c->stage_in[1], (n ? n : 1) * 32))) return rc;
     if (n) {
-        P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[0].p, points, n * psz, cudaMemcpyHostToDevice, c->stream));
-        P2B_CUDA(c, cudaMemcpyAsync(c->stage_in[1].p, scalars, n * 32, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = io_h2d(c, c->stage_in[0].p, points, n * psz, c->stream))) return rc;
+        if ((rc = io_h2d(c, c->stage_in[1].p, scalars, n * 32, c->stream))) return rc;
     }
     return msm_run(c, g2, c->stage_in[0].p, c->stage_in[1].p, n, out);
 }

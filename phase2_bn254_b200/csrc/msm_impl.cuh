@@ -25,6 +25,10 @@
 #include "xyzz.cuh"
 #include "p2b_internal.h"
 
+#ifndef P2B_ACC_DEFAULT_VARIANT
+#define P2B_ACC_DEFAULT_VARIANT 0
+#endif
+
 namespace p2b {
 
 // NOTE: the reduction kernels call the inlined adds from as few call sites as possible (every site is ~3k SASS
@@ -280,13 +284,35 @@ template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc
     q.y = cneg(q.y, (ent & 1u) != 0);
     acc = xyzz_madd(acc, q);
 }
-#ifndef P2B_ACC_MIN_BLOCKS
-#define P2B_ACC_MIN_BLOCKS 1
-#endif
-template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
+// Bucket accumulation, one thread per bucket.  VARIANT (tuning, selected at run time by P2B_ACC_VARIANT; all give the same sums):
+//   0  the round-1 loop: entry -> gather -> mixed add, nothing in flight across iterations
+//   1  software pipeline: the point of entry e+1 and the index of entry e+2 are loaded while the mixed add of entry e runs
+//      (each gather is a dependent pair of loads -- list entry, then a random 64 / 128 B point from HBM -- about 1.5 us of
+//      latency that 3 warps per scheduler do not always cover)
+//   2  variant 1 + the two squarings of the mixed add on the dedicated squaring routine
+//   3  variant 1 at 4 blocks per SM (<= 128 registers)
+template <class F, int VARIANT> struct AccBounds { static constexpr int MIN_BLOCKS = VARIANT == 3 ? 4 : (VARIANT == 0 ? 1 : 3); };
+template <class F> __device__ __forceinline__ void load_point_words(uint32_t *w, const uint32_t *aff, uint32_t ent) {
+    ldw<Wire<F>::WORDS_UNCOMPRESSED>(w, aff + (size_t)(ent >> 1) * Wire<F>::WORDS_UNCOMPRESSED);
+}
+template <class F, bool SQ> __device__ __forceinline__ void accumulate_words(Xyzz<F> &acc, const uint32_t *w, uint32_t ent) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < WU; j++) any |= w[j];
+    if (!any) return;                                          // point at infinity contributes nothing
+    Aff<F> q;
+#pragma unroll
+    for (int j = 0; j < W; j++) { set_word(q.x, j, w[j]); set_word(q.y, j, w[W + j]); }
+    q.y = cneg(q.y, (ent & 1u) != 0);
+    acc = SQ ? xyzz_madd_sq(acc, q) : xyzz_madd(acc, q);
+}
+template <class F, int VARIANT>
+__global__ void __launch_bounds__(128, AccBounds<F, VARIANT>::MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
                                                                            MsmGeom g, uint32_t *buckets, int first, uint32_t slot_lo,
                                                                            uint32_t slot_cnt, MsmHeavy hv, unsigned long long *err,
                                                                            const uint32_t *perm) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     // slots [slot_lo, slot_lo + slot_cnt) = the (window, bucket) pairs of one window group; `offsets` is that group's table;
     // perm lists the group's slots by decreasing size
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < slot_cnt; t += gridDim.x * blockDim.x) {
@@ -299,8 +325,27 @@ template <class F> __global__ void __launch_bounds__(128, P2B_ACC_MIN_BLOCKS) k_
             acc = load_xyzz<F>(buckets, gb);
         }
         const uint32_t mine = hi - lo > hv.seg ? lo + hv.seg : hi;
+        if constexpr (VARIANT == 0) {
 #pragma unroll 1
-        for (uint32_t e = lo; e < mine; e++) accumulate_entry<F>(acc, aff, __ldg(sorted + e));
+            for (uint32_t e = lo; e < mine; e++) accumulate_entry<F>(acc, aff, __ldg(sorted + e));
+        } else {
+            if (lo < mine) {
+                uint32_t ent = __ldg(sorted + lo), ent1 = lo + 1 < mine ? __ldg(sorted + lo + 1) : 0u;
+                uint32_t w[WU];
+                load_point_words<F>(w, aff, ent);
+#pragma unroll 1
+                for (uint32_t e = lo; e < mine; e++) {
+                    uint32_t wn[WU];
+                    const uint32_t ent2 = e + 2 < mine ? __ldg(sorted + e + 2) : 0u;
+                    if (e + 1 < mine) load_point_words<F>(wn, aff, ent1);      // in flight during the mixed add below
+                    accumulate_words<F, VARIANT == 2>(acc, w, ent);
+#pragma unroll
+                    for (int j = 0; j < WU; j++) w[j] = wn[j];
+                    ent = ent1;
+                    ent1 = ent2;
+                }
+            }
+        }
         store_xyzz<F>(buckets, gb, acc);
         if (mine < hi) {                                       // overflow: hand the tail to k_msm_heavy
             const uint32_t nit = (hi - mine + hv.chunk - 1) / hv.chunk;
@@ -734,8 +779,16 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         const int agrid = (int)((slot_cnt + 127) / 128);
         prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
         P2B_CUDA(c, cudaMemsetAsync(hv.counters, 0, 8, C));
-        k_msm_accumulate<F><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, (phase & MSM_FIRST) != 0, slot_lo, slot_cnt, hv, c->d_err,
-                                                  perm + slot_lo);
+        {
+            static const int variant = [] { const char *e = getenv("P2B_ACC_VARIANT"); return e ? atoi(e) : P2B_ACC_DEFAULT_VARIANT; }();
+            const int fst = (phase & MSM_FIRST) != 0;
+#define P2B_ACC_LAUNCH(V) k_msm_accumulate<F, V><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, fst, slot_lo, slot_cnt, hv, c->d_err, perm + slot_lo)
+            if (W != 8 || variant == 0) P2B_ACC_LAUNCH(0);      // G2 keeps the round-1 loop until its variants are measured
+            else if (variant == 1) { if constexpr (W == 8) P2B_ACC_LAUNCH(1); }
+            else if (variant == 2) { if constexpr (W == 8) P2B_ACC_LAUNCH(2); }
+            else { if constexpr (W == 8) P2B_ACC_LAUNCH(3); }
+#undef P2B_ACC_LAUNCH
+        }
         if constexpr (W == 8) msm_launch_heavy_g1(c, aff, sorted, buckets, hv);
         else msm_launch_heavy_g2(c, aff, sorted, buckets, hv);
         prof_end(c, P2B_PROF_MSM_ACCUMULATE, 3);

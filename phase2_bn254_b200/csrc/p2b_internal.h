@@ -12,6 +12,7 @@ namespace p2b {
 // device-side error word: min over (index << 8 | kind << 4 | sub); ~0 = no error
 static constexpr unsigned long long ERR_NONE = ~0ull;
 
+struct HostIO;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -33,9 +34,8 @@ struct Ctx {
     unsigned long long *h_err = nullptr;   // pinned mirror
     // growable device scratch
     DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, fft_tw, gtable, gfft;
-    // pinned host staging for pageable caller buffers
-    void *h_pin[2] = {nullptr, nullptr};
-    size_t h_pin_cap[2] = {0, 0};
+    // pinned staging rings + copy threads for pageable caller buffers (hostio.cu), created on first use
+    HostIO *io = nullptr;
     cudaEvent_t ev[8] = {};
     // profiling (p2b_profile_enable): CUDA-event brackets around the dominant kernels, on `stream`
     bool prof = false;
@@ -58,6 +58,13 @@ int ctx_collect_error(Ctx *c);
 // brackets `kernels` launches queued between prof_begin / prof_end with timing events (no-ops unless profiling)
 void prof_begin(Ctx *c, int slot, cudaStream_t stream = nullptr);   // nullptr: c->stream
 void prof_end(Ctx *c, int slot, int kernels, cudaStream_t stream = nullptr);
+
+// ---- hostio.cu: copies between CALLER buffers (pinned or pageable, e.g. the mmaps of the reference's binaries) and the device
+int io_h2d(Ctx *c, void *d_dst, const void *h_src, size_t bytes, cudaStream_t s);
+int io_d2h(Ctx *c, void *h_dst, const void *d_src, size_t bytes, cudaStream_t s);
+int io_flush(Ctx *c);        // all staged D2H bytes have reached the caller's buffer (after the streams have drained)
+void io_destroy(Ctx *c);
+void io_stats(Ctx *c, uint64_t *staged_in, uint64_t *staged_out);
 
 #define P2B_CUDA(c, call)                                     \
     do {                                                      \

@@ -157,7 +157,7 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
     char *sin = (char *)c->stage_in[0].p;
     uint32_t *A = (uint32_t *)c->gfft.p, *B = (uint32_t *)((char *)c->gfft.p + b_off), *R = (uint32_t *)((char *)c->gfft.p + r_off);
     if (nnz) {
-        P2B_CUDA(c, cudaMemcpyAsync(sin, bases, n_bases * psz, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = io_h2d(c, sin, bases, n_bases * psz, c->stream))) return rc;
         if (!all_general) {
             P2B_CUDA(c, cudaMemcpyAsync(sin + src_off, src.data(), nnz * 4, cudaMemcpyHostToDevice, c->stream));
             P2B_CUDA(c, cudaMemcpyAsync(sin + kind_off, kind.data(), nnz, cudaMemcpyHostToDevice, c->stream));
@@ -224,7 +224,7 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
         cur_pts = next_pts;
         next_pts = next_pts == B ? A : B;
     }
-    P2B_CUDA(c, cudaMemcpyAsync(out, c->stage_out[0].p, n_rows * psz, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = io_d2h(c, out, c->stage_out[0].p, n_rows * psz, c->stream))) return rc;
     P2B_CUDA(c, cudaGetLastError());
     return ctx_collect_error(c);
 }

@@ -49,6 +49,20 @@ template <class F> P2B_HD Xyzz<F> xyzz_madd(const Xyzz<F> &p, const Aff<F> &q) {
     Xyzz<F> qa; qa.x = q.x; qa.y = q.y; qa.zz = FieldTraits<F>::one(); qa.zzz = FieldTraits<F>::one();
     return select(p_inf, qa, r);
 }
+// the same with the two squarings on the dedicated squaring routine (tuning variant of the bucket accumulation)
+template <class F> P2B_HD Xyzz<F> xyzz_madd_sq(const Xyzz<F> &p, const Aff<F> &q) {
+    F u2 = mul(q.x, p.zz), s2 = mul(q.y, p.zzz);
+    F pp_ = sub(u2, p.x), rr = sub(s2, p.y);
+    F pp = sqr_ded(pp_), ppp = mul(pp_, pp), qq = mul(p.x, pp);
+    Xyzz<F> r;
+    r.x = sub(sub(sub(sqr_ded(rr), ppp), qq), qq);
+    r.y = sub(mul(rr, sub(qq, r.x)), mul(p.y, ppp));
+    r.zz = mul(p.zz, pp); r.zzz = mul(p.zzz, ppp);
+    bool p_inf = is_zero(p.zz);
+    if (!p_inf & is_zero(pp_) & is_zero(rr)) r = xyzz_dbl_aff(q);
+    Xyzz<F> qa; qa.x = q.x; qa.y = q.y; qa.zz = FieldTraits<F>::one(); qa.zzz = FieldTraits<F>::one();
+    return select(p_inf, qa, r);
+}
 // add-2008-s, complete
 template <class F> P2B_HD Xyzz<F> xyzz_add(const Xyzz<F> &p, const Xyzz<F> &q) {
     F u1 = mul(p.x, q.zz), u2 = mul(q.x, p.zz), s1 = mul(p.y, q.zzz), s2 = mul(q.y, p.zzz);

@@ -30,7 +30,7 @@ SYMBOLS = [
     "p2b_g1_group_fft", "p2b_g2_group_fft", "p2b_pot_radix_file_size", "p2b_pot_prepare_phase2",
     "p2b_g1_sparse_mul", "p2b_g2_sparse_mul",
     "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
-    "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants",
+    "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants", "p2b_io_stats",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -106,6 +106,8 @@ def load():
         getattr(lib, name).argtypes = [u8p] * (1 if name == "p2b_pairing_constants" else 2)
     lib.p2b_host_g1_mul.argtypes = [u8p, u8p, u8p]
     lib.p2b_host_g2_mul.argtypes = [u8p, u8p, u8p]
+    lib.p2b_io_stats.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    lib.p2b_io_stats.restype = None
     lib.p2b_profile_enable.argtypes = [vp, i32]
     lib.p2b_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     _lib = lib
@@ -259,6 +261,12 @@ class Context:
 
     def sync(self):
         self._check(self.lib.p2b_sync(self.h))
+
+    def io_stats(self):
+        """(H2D bytes, D2H bytes) of caller buffers that were pageable and went through the pinned staging rings."""
+        a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self.lib.p2b_io_stats(self.h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
 
     def profile(self, on=True):
         """Bracket the dominant kernels with CUDA events on the ctx stream (and reset the counters)."""
