@@ -143,7 +143,9 @@ int p2b_pot_decompress(p2b_ctx *ctx, const uint8_t *response, uint64_t response_
                        uint32_t shard_count);
 /* Bulk point codec (no scalar multiplication): out[i] = in[i] re-encoded.  Decompression (square roots), checked
  * deserialisation (P2B_CHECK_INPUT = is_on_curve, ec.rs:133-148; the point reads of Parameters::read,
- * bellman/src/groth16/mod.rs:287-383) and compression.  Same error reporting as the batch_mul entry points. */
+ * bellman/src/groth16/mod.rs:287-383) and compression.  Same error reporting as the batch_mul entry points.
+ * out == NULL: validation only (every point is decoded and checked on the device, nothing is copied back) -- the verifier's
+ * read of a chunk it only needs to be well-formed (batched_accumulator.rs:398-410). */
 int p2b_g1_recode(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, int in_enc, int out_enc, int flags);
 int p2b_g2_recode(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, size_t n, int in_enc, int out_enc, int flags);
 /* MPCParameters::contribute over the serialized parameters (`MPCParameters::write` format).  The RNG-derived values
@@ -162,6 +164,31 @@ int p2b_g1_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32,
 int p2b_g2_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32, size_t n, uint8_t *out);
 int p2b_g1_msm_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n, uint8_t *out_host);
 int p2b_g2_msm_dev(p2b_ctx *ctx, const void *d_points, const void *d_scalars_be32, size_t n, uint8_t *out_host);
+/* The verifier's random linear combinations in ONE pass (next row):
+ *   merge_pairs(v1, v2)  = (sum rho_i v1_i, sum rho_i v2_i)      powersoftau/src/utils.rs:112-130, phase2/src/utils.rs:59-105
+ *   power_pairs(v)       = merge_pairs(v[..n-1], v[1..])          powersoftau/src/utils.rs:133-135
+ * One upload, one decode, one counting sort of the shared scalars and one walk of the sorted entries feed TWO bucket sets
+ * (every entry costs two mixed adds; for power_pairs both points of an entry are adjacent in memory).
+ *   scalars_be32      n x 32 B big-endian canonical coefficients, or NULL: the coefficients are then generated ON THE DEVICE,
+ *                     coefficient i = bytes [32 i, 32 i + 32) of the ChaCha20 keystream (RFC 7539 block function; key = seed,
+ *                     64-bit block counter in state words 12-13, words 14-15 zero) read as a big-endian integer and cleared
+ *                     above scalar_bits bits -- the reference draws `Fr::rand(thread_rng())` per element; pass 32 bytes of
+ *                     OS entropy as the seed.  p2b_random_scalars returns the same values for tests and audits.
+ *   scalar_bits       upper bound promised for every coefficient (64..253 when generated, 0 = any canonical scalar when given);
+ *                     the windows only cover that many bits (128-bit coefficients halve the work, soundness error 2^-128).
+ *   in_enc            P2B_ENC_UNCOMPRESSED or P2B_ENC_COMPRESSED (decompressed on the device, as read_chunk does on the host)
+ *   flags             P2B_CHECK_INPUT (is_on_curve, CheckForCorrectness::Yes), P2B_REJECT_INFINITY (read_chunk's rule)
+ * p2b_*_power_pairs reads n_points points and combines n_points - 1 terms. */
+int p2b_g1_msm_pair(p2b_ctx *ctx, const uint8_t *points_a, const uint8_t *points_b, const uint8_t *scalars_be32, size_t n,
+                    const uint8_t seed[32], uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]);
+int p2b_g2_msm_pair(p2b_ctx *ctx, const uint8_t *points_a, const uint8_t *points_b, const uint8_t *scalars_be32, size_t n,
+                    const uint8_t seed[32], uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]);
+int p2b_g1_power_pairs(p2b_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars_be32, const uint8_t seed[32],
+                       uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]);
+int p2b_g2_power_pairs(p2b_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars_be32, const uint8_t seed[32],
+                       uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]);
+/* the device-generated coefficients [first_index, first_index + n) of `seed`, as 32-byte big-endian values (host buffer) */
+int p2b_random_scalars(p2b_ctx *ctx, const uint8_t seed[32], uint64_t first_index, size_t n, uint32_t scalar_bits, uint8_t *out);
 /* multi-GPU: the MSM shards by point range; each rank's result is an ordinary (affine, uncompressed) point, the
  * ranks exchange the 64 / 128-byte results (NCCL all-gather by the caller) and every rank adds them locally:
  * out = sum of `count` uncompressed points (infinity allowed). */

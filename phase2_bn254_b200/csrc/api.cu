@@ -130,7 +130,7 @@ static int run_host_job(Ctx *c, const HostJob &j) {
         P2B_CUDA(c, cudaEventRecord(ev_cdone[b], c->stream));
         // D2H
         P2B_CUDA(c, cudaStreamWaitEvent(c->copy_out, ev_cdone[b], 0));
-        if ((rc = io_d2h(c, j.out + off * osz, c->stage_out[b].p, m * osz, c->copy_out))) return rc;
+        if (j.out && (rc = io_d2h(c, j.out + off * osz, c->stage_out[b].p, m * osz, c->copy_out))) return rc;   // out == NULL: validation only
         P2B_CUDA(c, cudaEventRecord(ev_odone[b], c->copy_out));
     }
     // the next job may reuse both staging pairs: make the compute stream wait for the last two D2H copies,
@@ -174,7 +174,7 @@ static int host_batch(Ctx *c, int g2, const uint8_t *in, uint8_t *out, size_t n,
 }
 
 static int host_recode(Ctx *c, int g2, const uint8_t *in, uint8_t *out, size_t n, int in_enc, int out_enc, int flags) {
-    if (!in || !out) return ctx_fail(c, P2B_EARG, "null buffer");
+    if (!in) return ctx_fail(c, P2B_EARG, "null buffer");      // out may be NULL: decode + checks only, nothing is copied back
     HostJob j;
     memset(&j, 0, sizeof j);
     j.g2 = g2; j.in = in; j.out = out; j.n = n; j.in_enc = in_enc; j.out_enc = out_enc; j.flags = flags;
@@ -503,7 +503,7 @@ void p2b_destroy(p2b_ctx *h) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     io_destroy(c);
     DevBuf *bufs[] = {&c->jac, &c->prefix, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1], &c->scal,
-                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->fft_tw, &c->gtable, &c->gfft};
+                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->msm_f, &c->fft_tw, &c->gtable, &c->gfft};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &sl : c->prof_slot)
         for (auto &e : sl.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }

@@ -2,25 +2,42 @@
 #include "msm_impl.cuh"
 
 namespace p2b {
-int msm_typed_g2(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire, size_t geom_n,
-                 int phase, uint64_t err_base, size_t total_n);
+int msm_typed_g2(Ctx *c, const MsmJob &j);
+static int msm_typed_any(Ctx *c, int g2, const MsmJob &j) { return g2 ? msm_typed_g2(c, j) : msm_typed<Fq>(c, j); }
 
-// result: uncompressed wire bytes in device memory c->misc (first 128 bytes)
-static int msm_run(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, uint8_t *out_host) {
-    int rc;
-    if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
-    uint32_t *d_out = (uint32_t *)c->misc.p;
-    rc = g2 ? msm_typed_g2(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0, 0)
-            : msm_typed<Fq>(c, d_points, d_scalars, n, d_out, n, MSM_FIRST | MSM_LAST, 0);
-    if (rc) return rc;
-    P2B_CUDA(c, cudaMemcpyAsync(out_host, d_out, g2 ? 128 : 64, cudaMemcpyDeviceToHost, c->stream));
-    return ctx_collect_error(c);
-}
+// One call of the MSM family.  Buffers are HOST buffers unless `dev`.
+struct MsmCall {
+    int g2 = 0;
+    bool dev = false;
+    const uint8_t *points = nullptr, *points_b = nullptr;   // points_b: MSM_PAIR_SEPARATE
+    const uint8_t *scalars = nullptr;                       // n x 32 B big-endian; nullptr: generated on the device from `seed`
+    size_t n = 0;                                           // TERMS (a shifted pair reads n + 1 points)
+    int pair = MSM_SINGLE;
+    int in_enc = P2B_ENC_UNCOMPRESSED;                      // wire encoding of the points (uncompressed / compressed)
+    int flags = 0;                                          // P2B_CHECK_INPUT, P2B_REJECT_INFINITY
+    const uint8_t *seed = nullptr;
+    uint32_t scalar_bits = 0;
+    uint8_t *out_a = nullptr, *out_b = nullptr;
+};
 
 static int msm_begin(Ctx *c) {
     P2B_CUDA(c, cudaSetDevice(c->device));
     c->last_error.clear();
     P2B_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream));
+    return P2B_OK;
+}
+static ChaKey cha_key(const uint8_t *seed) {
+    ChaKey k;
+    for (int i = 0; i < 8; i++) k.k[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    return k;
+}
+static int random_scalars_dev(Ctx *c, uint32_t *d_scalars, size_t n, uint64_t first, const uint8_t *seed, uint32_t bits, cudaStream_t s) {
+    if (!n) return P2B_OK;
+    int grid = (int)((n / 2 + 256) / 256);
+    if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+    k_msm_random_scalars<<<grid, 256, 0, s>>>(d_scalars, n, first, cha_key(seed), bits);
+    c->launches++;
+    P2B_CUDA(c, cudaGetLastError());
     return P2B_OK;
 }
 
@@ -33,60 +50,107 @@ static size_t msm_stream_chunk() {       // P2B_MSM_STREAM_CHUNK=<terms>: test h
     long v = e ? atol(e) : 0;
     return v > 0 ? (size_t)v : 0;
 }
-static int msm_host_streamed(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
+
+static int msm_call(Ctx *c, const MsmCall &a) {
+    const bool pair = a.pair != MSM_SINGLE;
+    if (!a.out_a || (pair && !a.out_b)) return ctx_fail(c, P2B_EARG, "null output");
+    if (a.n && (!a.points || (a.pair == MSM_PAIR_SEPARATE && !a.points_b))) return ctx_fail(c, P2B_EARG, "null buffer");
+    if (!a.scalars && a.n) {
+        if (!a.seed) return ctx_fail(c, P2B_EARG, "need scalars or a seed for device-generated ones");
+        if (a.scalar_bits < 64 || a.scalar_bits > 253) return ctx_fail(c, P2B_EARG, "scalar_bits must be in [64, 253] for device-generated scalars");
+    }
+    if (a.scalar_bits > 253) return ctx_fail(c, P2B_EARG, "scalar_bits must be <= 253 (0 = any canonical scalar)");
+    if (a.in_enc != P2B_ENC_UNCOMPRESSED && a.in_enc != P2B_ENC_COMPRESSED) return ctx_fail(c, P2B_EARG, "bad encoding");
+    if (a.dev && a.in_enc != P2B_ENC_UNCOMPRESSED) return ctx_fail(c, P2B_EARG, "device entry points take uncompressed points");
+    int rc = msm_begin(c);
+    if (rc) return rc;
+    const size_t psz = a.g2 ? 128 : 64, isz = enc_size(a.g2, a.in_enc);
+    const size_t extra = a.pair == MSM_PAIR_SHIFTED ? 1 : 0;
     const size_t ov = msm_stream_chunk();
-    const size_t psz = g2 ? 128 : 64, chunk = ov ? ov : MSM_STREAM_CHUNK;
-    int rc;
-    for (int b = 0; b < 2; b++)
-        if ((rc = dev_reserve(c, c->stage_in[b], chunk * (psz + 32)))) return rc;
+    const bool streamed = !a.dev && a.n > (ov ? ov : MSM_STREAM_MIN);
+    const size_t chunk = streamed ? (ov ? ov : MSM_STREAM_CHUNK) : (a.n ? a.n : 1);
     if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
     uint32_t *d_out = (uint32_t *)c->misc.p;
+    // staging per buffer: points A (chunk + 1), points B (chunk), scalars (chunk)
+    const size_t off_b = (chunk + 1) * isz, off_s = off_b + (a.pair == MSM_PAIR_SEPARATE ? chunk * isz : 0);
+    const size_t stage_bytes = off_s + chunk * 32;
+    const int nbuf = streamed ? 2 : 1;
+    if (!a.dev || !a.scalars)
+        for (int b = 0; b < nbuf; b++)
+            if ((rc = dev_reserve(c, c->stage_in[b], stage_bytes))) return rc;
+    const bool compressed = a.in_enc == P2B_ENC_COMPRESSED;
+    if (compressed && (rc = dev_reserve(c, c->msm_f, (chunk + 1) * psz * (a.pair == MSM_PAIR_SEPARATE ? 2 : 1)))) return rc;
     cudaEvent_t *ev_in = c->ev, *ev_done = c->ev + 2;
     P2B_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    cudaStream_t CP = streamed ? c->copy_in : c->stream;
     // chunk sizes double from 1/8 of the maximum (1/8, 1/8, 1/4, 1/2, 1, 1, ..): the GPU starts after a short copy, and
     // every later copy is hidden behind the work on the terms already on the device
-    size_t off = 0, next = chunk / 8 ? chunk / 8 : 1;
-    for (size_t ci = 0; off < n; ci++) {
-        const int b = (int)(ci & 1);
+    size_t off = 0, next = streamed ? (chunk / 8 ? chunk / 8 : 1) : chunk;
+    const int check = ((a.flags & P2B_CHECK_INPUT) ? 1 : 0) | ((a.flags & P2B_REJECT_INFINITY) ? 2 : 0);
+    for (size_t ci = 0; off < a.n || ci == 0; ci++) {
+        const int b = (int)(ci & 1) % nbuf;
         size_t m = next;
         if (ci >= 1 && next < chunk) next = next * 2 < chunk ? next * 2 : chunk;
-        if (m > n - off) m = n - off;
-        P2B_CUDA(c, cudaStreamWaitEvent(c->copy_in, ci >= 2 ? ev_done[b] : c->ev[6], 0));
-        char *d_pts = (char *)c->stage_in[b].p, *d_sc = d_pts + chunk * psz;
-        if ((rc = io_h2d(c, d_pts, points + off * psz, m * psz, c->copy_in))) return rc;
-        if ((rc = io_h2d(c, d_sc, scalars + off * 32, m * 32, c->copy_in))) return rc;
-        P2B_CUDA(c, cudaEventRecord(ev_in[b], c->copy_in));
-        P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
-        const int phase = (ci == 0 ? MSM_FIRST : 0) | (off + m == n ? MSM_LAST : 0);
-        rc = g2 ? msm_typed_g2(c, d_pts, d_sc, m, d_out, chunk, phase, off, n) : msm_typed<Fq>(c, d_pts, d_sc, m, d_out, chunk, phase, off, n);
-        if (rc) return rc;
-        P2B_CUDA(c, cudaEventRecord(ev_done[b], c->stream));
+        if (m > a.n - off) m = a.n - off;
+        const void *d_pts = nullptr, *d_pts_b = nullptr, *d_sc = nullptr;
+        if (a.dev) {
+            d_pts = a.points; d_pts_b = a.points_b; d_sc = a.scalars;
+        } else {
+            if (streamed) P2B_CUDA(c, cudaStreamWaitEvent(CP, ci >= 2 ? ev_done[b] : c->ev[6], 0));
+            char *st = (char *)c->stage_in[b].p;
+            if ((m + extra) && (rc = io_h2d(c, st, a.points + off * isz, (m + extra) * isz, CP))) return rc;
+            d_pts = st;
+            if (a.pair == MSM_PAIR_SEPARATE) {
+                if (m && (rc = io_h2d(c, st + off_b, a.points_b + off * isz, m * isz, CP))) return rc;
+                d_pts_b = st + off_b;
+            }
+            if (a.scalars) {
+                if (m && (rc = io_h2d(c, st + off_s, a.scalars + off * 32, m * 32, CP))) return rc;
+                d_sc = st + off_s;
+            }
+        }
+        if (!a.scalars) {
+            char *st = (char *)c->stage_in[b].p;
+            if ((rc = random_scalars_dev(c, (uint32_t *)(st + off_s), m, off, a.seed, a.scalar_bits, CP))) return rc;
+            d_sc = st + off_s;
+        }
+        if (streamed) {
+            P2B_CUDA(c, cudaEventRecord(ev_in[b], CP));
+            P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
+        }
+        MsmJob j;
+        j.n = m; j.d_scalars = d_sc; j.d_out_wire = d_out; j.geom_n = chunk; j.err_base = off; j.total_n = streamed ? a.n : 0;
+        j.phase = (ci == 0 ? MSM_FIRST : 0) | (off + m == a.n ? MSM_LAST : 0);
+        j.pair = a.pair; j.scalar_bits = a.scalar_bits;
+        if (compressed) {     // decompress (square root per point) into raw Montgomery form; the MSM's prepare kernel then only copies
+            ScalarSpec sc;
+            memset(&sc, 0, sizeof sc);
+            sc.mode = 3;
+            char *raw = (char *)c->msm_f.p;
+            if ((m + extra) && (rc = launch_batch_mul(c, a.g2, d_pts, raw, m + extra, sc, P2B_ENC_COMPRESSED, P2B_ENC_RAW_MONT_LE,
+                                                      a.flags & P2B_REJECT_INFINITY, off))) return rc;
+            j.d_points = raw;
+            if (a.pair == MSM_PAIR_SEPARATE) {
+                char *raw_b = raw + (chunk + 1) * psz;
+                if (m && (rc = launch_batch_mul(c, a.g2, d_pts_b, raw_b, m, sc, P2B_ENC_COMPRESSED, P2B_ENC_RAW_MONT_LE,
+                                                a.flags & P2B_REJECT_INFINITY, off))) return rc;
+                j.d_points_b = raw_b;
+            }
+            j.in_enc = ENC_RAW_MONT_LE;
+            j.check = 0;
+        } else {
+            j.d_points = d_pts; j.d_points_b = d_pts_b; j.in_enc = ENC_UNCOMPRESSED; j.check = check;
+        }
+        if ((rc = msm_typed_any(c, a.g2, j))) return rc;
+        if (streamed) P2B_CUDA(c, cudaEventRecord(ev_done[b], c->stream));
         off += m;
+        if (off >= a.n) break;
     }
-    P2B_CUDA(c, cudaMemcpyAsync(out, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
+    P2B_CUDA(c, cudaMemcpyAsync(a.out_a, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
+    if (pair) P2B_CUDA(c, cudaMemcpyAsync(a.out_b, d_out + psz / 4, psz, cudaMemcpyDeviceToHost, c->stream));
     return ctx_collect_error(c);
 }
 
-static int msm_host(Ctx *c, int g2, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
-    if (!out || (n && (!points || !scalars))) return ctx_fail(c, P2B_EARG, "null buffer");
-    int rc = msm_begin(c);
-    if (rc) return rc;
-    if (n > (msm_stream_chunk() ? msm_stream_chunk() : MSM_STREAM_MIN)) return msm_host_streamed(c, g2, points, scalars, n, out);
-    const size_t psz = g2 ? 128 : 64;
-    if ((rc = dev_reserve(c, c->stage_in[0], (n ? n : 1) * psz))) return rc;
-    if ((rc = dev_reserve(c, c->stage_in[1], (n ? n : 1) * 32))) return rc;
-    if (n) {
-        if ((rc = io_h2d(c, c->stage_in[0].p, points, n * psz, c->stream))) return rc;
-        if ((rc = io_h2d(c, c->stage_in[1].p, scalars, n * 32, c->stream))) return rc;
-    }
-    return msm_run(c, g2, c->stage_in[0].p, c->stage_in[1].p, n, out);
-}
-static int msm_dev(Ctx *c, int g2, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) {
-    if (!out || (n && (!d_points || !d_scalars))) return ctx_fail(c, P2B_EARG, "null buffer");
-    int rc = msm_begin(c);
-    if (rc) return rc;
-    return msm_run(c, g2, d_points, d_scalars, n, out);
-}
 static int sum_points(Ctx *c, int g2, const uint8_t *points, size_t count, uint8_t *out) {
     if (!out || (count && !points)) return ctx_fail(c, P2B_EARG, "null buffer");
     if (count > 65536) return ctx_fail(c, P2B_EARG, "sum_points: too many points");
@@ -103,21 +167,61 @@ static int sum_points(Ctx *c, int g2, const uint8_t *points, size_t count, uint8
     return ctx_collect_error(c);
 }
 
+static int random_scalars_host(Ctx *c, const uint8_t *seed, uint64_t first, size_t n, uint32_t bits, uint8_t *out) {
+    if (!seed || (n && !out)) return ctx_fail(c, P2B_EARG, "null buffer");
+    if (bits < 1 || bits > 253) return ctx_fail(c, P2B_EARG, "scalar_bits must be in [1, 253]");
+    int rc = msm_begin(c);
+    if (rc) return rc;
+    if ((rc = dev_reserve(c, c->stage_in[0], (n ? n : 1) * 32))) return rc;
+    if ((rc = random_scalars_dev(c, (uint32_t *)c->stage_in[0].p, n, first, seed, bits, c->stream))) return rc;
+    if ((rc = io_d2h(c, out, c->stage_in[0].p, n * 32, c->stream))) return rc;
+    return ctx_collect_error(c);
+}
+
 }  // namespace p2b
 
 using namespace p2b;
+static int single(p2b_ctx *h, int g2, bool dev, const void *points, const void *scalars, size_t n, uint8_t *out) {
+    if (!h) return P2B_EARG;
+    if (n && !scalars) return ctx_fail(&h->c, P2B_EARG, "null buffer");
+    MsmCall a;
+    a.g2 = g2; a.dev = dev; a.points = (const uint8_t *)points; a.scalars = (const uint8_t *)scalars; a.n = n; a.out_a = out;
+    return msm_call(&h->c, a);
+}
+static int pair_call(p2b_ctx *h, int g2, const uint8_t *pa, const uint8_t *pb, const uint8_t *scalars, size_t n, const uint8_t *seed,
+                     uint32_t bits, int in_enc, int flags, uint8_t *out_a, uint8_t *out_b, bool shifted) {
+    if (!h) return P2B_EARG;
+    MsmCall a;
+    a.g2 = g2; a.points = pa; a.points_b = pb; a.scalars = scalars; a.n = n; a.seed = seed; a.scalar_bits = bits;
+    a.in_enc = in_enc; a.flags = flags; a.out_a = out_a; a.out_b = out_b;
+    a.pair = shifted ? MSM_PAIR_SHIFTED : MSM_PAIR_SEPARATE;
+    return msm_call(&h->c, a);
+}
 extern "C" {
-int p2b_g1_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
-    return h ? msm_host(&h->c, 0, points, scalars, n, out) : P2B_EARG;
+int p2b_g1_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) { return single(h, 0, false, points, scalars, n, out); }
+int p2b_g2_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) { return single(h, 1, false, points, scalars, n, out); }
+int p2b_g1_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) { return single(h, 0, true, d_points, d_scalars, n, out); }
+int p2b_g2_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) { return single(h, 1, true, d_points, d_scalars, n, out); }
+int p2b_g1_msm_pair(p2b_ctx *h, const uint8_t *points_a, const uint8_t *points_b, const uint8_t *scalars, size_t n, const uint8_t seed[32],
+                    uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]) {
+    return pair_call(h, 0, points_a, points_b, scalars, n, seed, scalar_bits, in_enc, flags, out_a, out_b, false);
 }
-int p2b_g2_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) {
-    return h ? msm_host(&h->c, 1, points, scalars, n, out) : P2B_EARG;
+int p2b_g2_msm_pair(p2b_ctx *h, const uint8_t *points_a, const uint8_t *points_b, const uint8_t *scalars, size_t n, const uint8_t seed[32],
+                    uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]) {
+    return pair_call(h, 1, points_a, points_b, scalars, n, seed, scalar_bits, in_enc, flags, out_a, out_b, false);
 }
-int p2b_g1_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) {
-    return h ? msm_dev(&h->c, 0, d_points, d_scalars, n, out) : P2B_EARG;
+int p2b_g1_power_pairs(p2b_ctx *h, const uint8_t *points, size_t n_points, const uint8_t *scalars, const uint8_t seed[32], uint32_t scalar_bits,
+                       int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]) {
+    if (h && n_points < 1) return ctx_fail(&h->c, P2B_EARG, "power_pairs needs at least one point");
+    return pair_call(h, 0, points, nullptr, scalars, n_points - 1, seed, scalar_bits, in_enc, flags, out_a, out_b, true);
 }
-int p2b_g2_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) {
-    return h ? msm_dev(&h->c, 1, d_points, d_scalars, n, out) : P2B_EARG;
+int p2b_g2_power_pairs(p2b_ctx *h, const uint8_t *points, size_t n_points, const uint8_t *scalars, const uint8_t seed[32], uint32_t scalar_bits,
+                       int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]) {
+    if (h && n_points < 1) return ctx_fail(&h->c, P2B_EARG, "power_pairs needs at least one point");
+    return pair_call(h, 1, points, nullptr, scalars, n_points - 1, seed, scalar_bits, in_enc, flags, out_a, out_b, true);
+}
+int p2b_random_scalars(p2b_ctx *h, const uint8_t seed[32], uint64_t first_index, size_t n, uint32_t scalar_bits, uint8_t *out) {
+    return h ? random_scalars_host(&h->c, seed, first_index, n, scalar_bits, out) : P2B_EARG;
 }
 int p2b_g1_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[64]) {
     return h ? sum_points(&h->c, 0, points, count, out) : P2B_EARG;

@@ -26,7 +26,7 @@
 #include "p2b_internal.h"
 
 #ifndef P2B_ACC_DEFAULT_VARIANT
-#define P2B_ACC_DEFAULT_VARIANT 0
+#define P2B_ACC_DEFAULT_VARIANT 2
 #endif
 
 namespace p2b {
@@ -113,20 +113,68 @@ static __device__ __forceinline__ void report_err(unsigned long long *err, uint6
 }
 
 // ------------------------------------------------------------------------------------------------- kernels
-template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const uint32_t *wire, uint32_t *aff, size_t n, unsigned long long *err, uint64_t err_base) {
+template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const uint32_t *wire, uint32_t *aff, size_t n, unsigned long long *err, uint64_t err_base,
+                                                                        int in_enc, int check) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t w[WU];
         ldw<WU>(w, wire + i * WU);
         Aff<F> a;
         bool inf;
-        int rc = point_decode<F>(a, inf, w, ENC_UNCOMPRESSED, false);
+        int rc = point_decode<F>(a, inf, w, in_enc, (check & 1) != 0);     // in_enc: uncompressed wire, or RAW (already decoded)
         if (rc) { report_err(err, err_base + i, P2B_EDECODE, rc); inf = true; }
+        else if (inf && (check & 2)) report_err(err, err_base + i, P2B_EINFINITY_IN, 0);
         uint32_t o[WU];
         point_encode<F>(o, a, inf, ENC_RAW_MONT_LE);   // infinity = all-zero: skipped by the accumulator
         stw<WU>(aff + i * WU, o);
     }
 }
+
+// Random scalars generated on the device: scalar i = 32 bytes of the ChaCha20 keystream (RFC 7539 block function, 20
+// rounds) under `key`, block counter i / 2 in state words 12-13 (little-endian 64-bit), words 14-15 zero; the block's 64
+// bytes are two 32-byte big-endian scalars, cleared above `bits` bits (bits <= 253 < log2 r: always canonical).  Used for
+// the verifier's random linear combinations (powersoftau/src/utils.rs:118-124, phase2/src/utils.rs:76-85: `Fr::rand(rng)`
+// per element): the key comes from the host's CSPRNG, the 2 GB of coefficients of a 2^26-element check never cross PCIe.
+static __device__ __forceinline__ uint32_t rotl32(uint32_t v, int k) { return __funnelshift_l(v, v, k); }
+#define P2B_QR(a, b, c, d) a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); a += b; d ^= a; d = rotl32(d, 8); c += d; b ^= c; b = rotl32(b, 7);
+struct ChaKey { uint32_t k[8]; };
+static __global__ void __launch_bounds__(256) k_msm_random_scalars(uint32_t *scalars, size_t n, uint64_t first, ChaKey key, uint32_t bits) {
+    const size_t nblk = (n + (first & 1) + 1) / 2;               // blocks touched: scalars first .. first + n - 1
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t ctr = first / 2 + b;
+        uint32_t x[16], in[16];
+        in[0] = 0x61707865u; in[1] = 0x3320646eu; in[2] = 0x79622d32u; in[3] = 0x6b206574u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) in[4 + i] = key.k[i];
+        in[12] = (uint32_t)ctr; in[13] = (uint32_t)(ctr >> 32); in[14] = 0; in[15] = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = in[i];
+#pragma unroll 1
+        for (int r = 0; r < 10; r++) {
+            P2B_QR(x[0], x[4], x[8], x[12]) P2B_QR(x[1], x[5], x[9], x[13]) P2B_QR(x[2], x[6], x[10], x[14]) P2B_QR(x[3], x[7], x[11], x[15])
+            P2B_QR(x[0], x[5], x[10], x[15]) P2B_QR(x[1], x[6], x[11], x[12]) P2B_QR(x[2], x[7], x[8], x[13]) P2B_QR(x[3], x[4], x[9], x[14])
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] += in[i];
+        // keystream bytes = little-endian words; scalar = those 32 bytes read as a big-endian integer, top bits cleared
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint64_t idx = 2 * ctr + h;
+            if (idx < first || idx >= first + n) continue;
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t be = bswap32(x[8 * h + j]);             // big-endian value of wire bytes 4j .. 4j+3
+                const int hi_bit = 256 - 32 * j;                 // this word holds integer bits [hi_bit - 32, hi_bit)
+                if ((int)bits <= hi_bit - 32) be = 0;
+                else if ((int)bits < hi_bit) be &= (1u << (bits - (hi_bit - 32))) - 1u;
+                w[j] = bswap32(be);                              // back to memory order
+            }
+            stw<8>(scalars + (size_t)(idx - first) * 8, w);
+        }
+    }
+}
+#undef P2B_QR
 
 static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars, size_t n, MsmGeom g, uint32_t *hist, unsigned long long *err, uint64_t err_base,
                                                              uint32_t w_lo, uint32_t w_hi) {
@@ -136,7 +184,14 @@ static __global__ void __launch_bounds__(256) k_msm_hist(const uint32_t *scalars
         Fr kc;
 #pragma unroll
         for (int j = 0; j < 8; j++) kc.l[j] = k[j];
-        if (w_lo == 0 && !is_canonical(kc)) report_err(err, err_base + i, P2B_EARG, 0);
+        if (w_lo == 0) {
+            bool bad = !is_canonical(kc);
+            const uint32_t total = g.nwin * g.c - g.nnarrow;       // bits covered by the windows (255 unless the caller bounded the scalars)
+            if (total < 255) {                                     // scalars must stay below 2^(total - 1)
+                for (uint32_t b = total - 1; b < 256; b++) bad |= ((k[b >> 5] >> (b & 31)) & 1u) != 0;
+            }
+            if (bad) report_err(err, err_base + i, P2B_EARG, 0);
+        }
         uint32_t carry = 0;
         for (uint32_t w = 0; w < w_hi; w++) {                  // the signed-digit carry needs the windows below w_lo too
             const uint32_t wd = win_width(g, w);
@@ -357,6 +412,51 @@ __global__ void __launch_bounds__(128, AccBounds<F, VARIANT>::MIN_BLOCKS) k_msm_
                 }
                 hv.hbuckets[hb] = make_uint4(gb, fi, nit, 0u);
             } else report_err(err, gb, P2B_ECUDA, 0);          // cannot happen: the capacities cover the worst case
+        }
+    }
+}
+
+// Pair mode: ONE sorted list of (term, sign) entries drives TWO bucket sets -- sum k_i A_i and sum k_i B_i for two point
+// arrays under the same scalars (merge_pairs, phase2/src/utils.rs:59-105; power_pairs = the same with B = A shifted by one
+// point, powersoftau/src/utils.rs:133-135, where both points of an entry sit next to each other in memory).  The sort, the
+// scalar traffic and the digit extraction are shared; every entry costs two mixed adds.  The whole bucket is walked by its
+// thread (no overflow hand-off: the scalars of these checks are the verifier's own random numbers, never skewed; any other
+// input is still summed correctly, only not load-balanced).
+template <class F>
+__global__ void __launch_bounds__(128, 2) k_msm_accumulate_pair(const uint32_t *aff_a, const uint32_t *aff_b, const uint32_t *offsets,
+                                                                const uint32_t *sorted, uint32_t *buckets_a, uint32_t *buckets_b, int first,
+                                                                uint32_t slot_lo, uint32_t slot_cnt, const uint32_t *perm) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < slot_cnt; t += gridDim.x * blockDim.x) {
+        const uint32_t idx = perm[t];
+        const uint32_t gb = slot_lo + idx;
+        const uint32_t lo = offsets[idx], hi = offsets[idx + 1];
+        if (!first && lo == hi) continue;
+        if constexpr (FieldTraits<F>::WORDS == 8) {
+            Xyzz<F> acc_a = xyzz_infinity<F>(), acc_b = xyzz_infinity<F>();
+            if (!first) {
+                acc_a = load_xyzz<F>(buckets_a, gb);
+                acc_b = load_xyzz<F>(buckets_b, gb);
+            }
+#pragma unroll 1
+            for (uint32_t e = lo; e < hi; e++) {
+                const uint32_t ent = __ldg(sorted + e);
+                accumulate_entry<F>(acc_a, aff_a, ent);
+                accumulate_entry<F>(acc_b, aff_b, ent);
+            }
+            store_xyzz<F>(buckets_a, gb, acc_a);
+            store_xyzz<F>(buckets_b, gb, acc_b);
+        } else {
+            // G2: one accumulator already takes the whole register file -- walk the (short, cached) list once per set
+#pragma unroll 1
+            for (int set = 0; set < 2; set++) {
+                const uint32_t *aff = set ? aff_b : aff_a;
+                uint32_t *bk = set ? buckets_b : buckets_a;
+                Xyzz<F> acc = xyzz_infinity<F>();
+                if (!first) acc = load_xyzz<F>(bk, gb);
+#pragma unroll 1
+                for (uint32_t e = lo; e < hi; e++) accumulate_entry<F>(acc, aff, __ldg(sorted + e));
+                store_xyzz<F>(bk, gb, acc);
+            }
         }
     }
 }
@@ -656,7 +756,7 @@ void msm_launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint
 // Width: the widest c <= 0.6 log2(n) + 3.5 that is minimal for its window count -- a fit to the sweeps on B200 with
 // size-ordered buckets (2^20 -> 15, 2^22 -> 16, 2^24 -> 17, 2^26 -> 19): more windows cost n mixed adds each, wider windows
 // lengthen the serial strip walk of the bucket reduction and leave the accumulation threads shorter lists.
-static inline MsmGeom msm_geometry(size_t n) {
+static inline MsmGeom msm_geometry(size_t n, uint32_t scalar_bits = 0) {
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     int target = (int)(0.6 * lg + 3.5);
@@ -666,15 +766,18 @@ static inline MsmGeom msm_geometry(size_t n) {
     }
     if (target < 6) target = 6;
     if (target > 20) target = 20;
+    // bits to cover: the scalar plus one bit of head-room for the signed-digit carry (255 for any canonical scalar)
+    const uint32_t total = scalar_bits && scalar_bits < 254 ? scalar_bits + 1 : 255;
+    if ((uint32_t)target > total) target = (int)total;
     MsmGeom g{};
     for (int c = target; c >= 2; c--) {
-        const uint32_t nwin = (255 + c - 1) / c;
-        if ((255 + nwin - 1) / nwin != (uint32_t)c) continue;       // fewer bits would do for this many windows
+        const uint32_t nwin = (total + c - 1) / c;
+        if ((total + nwin - 1) / nwin != (uint32_t)c) continue;       // fewer bits would do for this many windows
         g.c = (uint32_t)c;
         g.nwin = nwin;
         break;
     }
-    g.nnarrow = g.nwin * g.c - 255;
+    g.nnarrow = g.nwin * g.c - total;
     g.nb = 1u << (g.c - 1);
     g.nbk = g.nb + 1;
     g.strip = g.nb > 1024 ? g.nb / 1024 : 1;
@@ -682,32 +785,51 @@ static inline MsmGeom msm_geometry(size_t n) {
     return g;
 }
 
-// One MSM, or one chunk of a streamed MSM: `geom_n` (>= n) fixes the scratch sizes for all chunks;
-// MSM_FIRST starts fresh buckets, MSM_LAST runs the bucket / window reduction and writes the affine result.
+// One MSM, or one chunk of a streamed MSM.
 enum { MSM_FIRST = 1, MSM_LAST = 2 };
-template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_scalars, size_t n, uint32_t *d_out_wire,
-                                 size_t geom_n, int phase, uint64_t err_base, size_t total_n = 0) {
+enum { MSM_SINGLE = 0, MSM_PAIR_SHIFTED = 1, MSM_PAIR_SEPARATE = 2 };
+struct MsmJob {
+    const void *d_points = nullptr;     // n points (n + 1 for MSM_PAIR_SHIFTED: B_i = A_(i+1)); encoding `in_enc`
+    const void *d_points_b = nullptr;   // MSM_PAIR_SEPARATE: the second array
+    const void *d_scalars = nullptr;    // n x 32 bytes big-endian, canonical
+    size_t n = 0;
+    uint32_t *d_out_wire = nullptr;     // result (uncompressed wire); pair modes: result B follows at + WORDS_UNCOMPRESSED
+    size_t geom_n = 0;                  // >= n: fixes the scratch sizes for all chunks of a streamed MSM
+    int phase = MSM_FIRST | MSM_LAST;   // MSM_FIRST starts fresh buckets, MSM_LAST reduces and writes the result
+    uint64_t err_base = 0;
+    size_t total_n = 0;                 // size of the WHOLE sum (window widths follow it), 0 = geom_n
+    int pair = MSM_SINGLE;
+    int in_enc = ENC_UNCOMPRESSED;      // ENC_UNCOMPRESSED (wire) or ENC_RAW_MONT_LE (decoded by an earlier kernel)
+    int check = 0;                      // bit 0: is_on_curve on every point (CheckForCorrectness::Yes); bit 1: infinity is an error
+    uint32_t scalar_bits = 0;           // the caller guarantees scalars < 2^scalar_bits (0: any canonical scalar)
+};
+template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
     constexpr int W = FieldTraits<F>::WORDS, WU = Wire<F>::WORDS_UNCOMPRESSED;
+    const size_t n = j.n, geom_n = j.geom_n;
+    const bool pair = j.pair != MSM_SINGLE;
     if (geom_n >= ((size_t)1 << 31) || n > geom_n) return ctx_fail(c, P2B_EARG, "msm: chunk must be < 2^31 terms");
     // window widths follow the size of the WHOLE sum (total_n, when this call is one chunk of a streamed MSM); the scratch
     // buffers are sized for the largest chunk (geom_n)
-    MsmGeom g = msm_geometry(total_n ? total_n : (geom_n ? geom_n : 1));
+    MsmGeom g = msm_geometry(j.total_n ? j.total_n : (geom_n ? geom_n : 1), j.scalar_bits);
     const size_t cap_n = geom_n ? geom_n : 1;
     if ((uint64_t)g.nwin * cap_n >= (1ull << 32)) return ctx_fail(c, P2B_EARG, "msm: too many terms for one pass (use the host entry point, which streams)");
     const size_t nslots = (size_t)g.nwin * g.nbk;
     const size_t xy = (size_t)4 * W * 4;                       // bytes per XYZZ point
+    const size_t nsets = pair ? 2 : 1;
     int rc;
     // msm_a: affine Montgomery points ; msm_b: hist | offsets | cursor ; msm_c: sorted entries ; msm_d: buckets | s1 | s2 | wsum
-    if ((rc = dev_reserve(c, c->msm_a, cap_n * WU * 4))) return rc;
+    if ((rc = dev_reserve(c, c->msm_a, (nsets * cap_n + 1) * WU * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_b, (4 * nslots + 16 + nslots / SCAN_TILE + 8) * 4))) return rc;
     if ((rc = dev_reserve(c, c->msm_c, (size_t)g.nwin * cap_n * 4))) return rc;
     const size_t nred = (size_t)g.nwin * g.tpw;
-    if ((rc = dev_reserve(c, c->msm_d, (nslots + 2 * nred + g.nwin + (size_t)g.nwin * 96) * xy + (size_t)g.nwin * 4 + 64))) return rc;
+    if ((rc = dev_reserve(c, c->msm_d, (nsets * nslots + 2 * nred + g.nwin + (size_t)g.nwin * 96) * xy + (size_t)g.nwin * 4 + 64))) return rc;
     uint32_t *aff = (uint32_t *)c->msm_a.p;
+    uint32_t *aff_b = j.pair == MSM_PAIR_SHIFTED ? aff + WU : aff + (cap_n + 1) * WU;
     uint32_t *hist = (uint32_t *)c->msm_b.p, *cursor = hist + nslots, *offsets = cursor + nslots;   // offsets: nslots + one per group
     uint32_t *perm = offsets + nslots + 16, *tile_sums = perm + nslots;
     uint32_t *sorted = (uint32_t *)c->msm_c.p;
-    uint32_t *buckets = (uint32_t *)c->msm_d.p, *s1 = buckets + nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
+    uint32_t *buckets = (uint32_t *)c->msm_d.p, *buckets_b = buckets + nslots * 4 * W;
+    uint32_t *s1 = buckets + nsets * nslots * 4 * W, *s2 = s1 + nred * 4 * W, *wsum = s2 + nred * 4 * W;
     // overflow handling for skewed digit distributions (see MsmHeavy)
     MsmHeavy hv;
     uint32_t *size_hist = nullptr, *size_start = nullptr;
@@ -748,8 +870,14 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
     P2B_CUDA(c, cudaMemsetAsync(hist, 0, nslots * 4, S));
     P2B_CUDA(c, cudaMemsetAsync(size_hist, 0, ((size_t)hv.seg + 2) * 4, S));
     // the point decode is only needed by the accumulation: it runs on the compute stream, next to the first group's sort
-    k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)d_points, aff, n, c->d_err, err_base);
+    const size_t np_a = n + (j.pair == MSM_PAIR_SHIFTED ? 1 : 0);
+    k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)j.d_points, aff, np_a, c->d_err, j.err_base, j.in_enc, j.check);
     c->launches++;
+    if (j.pair == MSM_PAIR_SEPARATE) {
+        k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)j.d_points_b, aff_b, n, c->d_err, j.err_base, j.in_enc, j.check);
+        c->launches++;
+    }
+    const int fst = (j.phase & MSM_FIRST) != 0;
     for (uint32_t gi = 0; gi < ngroups; gi++) {
         // the first group is small: its sort is the only one that cannot hide behind an accumulation
         const uint32_t first_hi = g.nwin / 7 ? g.nwin / 7 : 1;
@@ -757,14 +885,14 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         const uint32_t w_lo = bounds[gi], w_hi = ngroups == 3 ? bounds[gi + 1] : g.nwin;
         const uint32_t slot_lo = w_lo * g.nbk, slot_cnt = (w_hi - w_lo) * g.nbk;
         uint32_t *offs = offsets + slot_lo + gi;
-        k_msm_hist<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, hist, c->d_err, err_base, w_lo, w_hi);
+        k_msm_hist<<<grid, 256, 0, S>>>((const uint32_t *)j.d_scalars, n, g, hist, c->d_err, j.err_base, w_lo, w_hi);
         {
             const uint32_t ntiles = (slot_cnt + SCAN_TILE - 1) / SCAN_TILE;
             k_msm_scan_tiles<<<ntiles, 256, 0, S>>>(hist + slot_lo, slot_cnt, tile_sums);
             k_msm_scan_tops<<<1, 32, 0, S>>>(tile_sums, ntiles, (uint32_t)((size_t)w_lo * cap_n));
             k_msm_scan_apply<<<ntiles, 256, 0, S>>>(hist + slot_lo, offs, cursor + slot_lo, slot_cnt, tile_sums, ntiles);
         }
-        k_msm_scatter<<<grid, 256, 0, S>>>((const uint32_t *)d_scalars, n, g, cursor, sorted, w_lo, w_hi);
+        k_msm_scatter<<<grid, 256, 0, S>>>((const uint32_t *)j.d_scalars, n, g, cursor, sorted, w_lo, w_hi);
         {   // order the group's buckets by size (see k_msm_size_hist)
             const int sgrid = (int)((slot_cnt + 255) / 256) < c->sm_count * 8 ? (int)((slot_cnt + 255) / 256) : c->sm_count * 8;
             k_msm_size_hist<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_hist);
@@ -778,12 +906,17 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         }
         const int agrid = (int)((slot_cnt + 127) / 128);
         prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
+        if (pair) {
+            k_msm_accumulate_pair<F><<<agrid, 128, 0, C>>>(aff, aff_b, offs, sorted, buckets, buckets_b, fst, slot_lo, slot_cnt, perm + slot_lo);
+            prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
+            c->launches += 9;
+            continue;
+        }
         P2B_CUDA(c, cudaMemsetAsync(hv.counters, 0, 8, C));
         {
             static const int variant = [] { const char *e = getenv("P2B_ACC_VARIANT"); return e ? atoi(e) : P2B_ACC_DEFAULT_VARIANT; }();
-            const int fst = (phase & MSM_FIRST) != 0;
 #define P2B_ACC_LAUNCH(V) k_msm_accumulate<F, V><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, fst, slot_lo, slot_cnt, hv, c->d_err, perm + slot_lo)
-            if (W != 8 || variant == 0) P2B_ACC_LAUNCH(0);      // G2 keeps the round-1 loop until its variants are measured
+            if (W != 8 || variant == 0) P2B_ACC_LAUNCH(0);      // G2 (255 registers already) keeps the plain loop
             else if (variant == 1) { if constexpr (W == 8) P2B_ACC_LAUNCH(1); }
             else if (variant == 2) { if constexpr (W == 8) P2B_ACC_LAUNCH(2); }
             else { if constexpr (W == 8) P2B_ACC_LAUNCH(3); }
@@ -794,15 +927,19 @@ template <class F> int msm_typed(Ctx *c, const void *d_points, const void *d_sca
         prof_end(c, P2B_PROF_MSM_ACCUMULATE, 3);
         c->launches += 11;
     }
-    if (!(phase & MSM_LAST)) {
+    if (!(j.phase & MSM_LAST)) {
         P2B_CUDA(c, cudaGetLastError());
         return P2B_OK;
     }
     prof_begin(c, P2B_PROF_MSM_REDUCE);
-    if constexpr (W == 8) msm_launch_reduce_g1(c, buckets, g, s1, s2, wsum, d_out_wire, nred);
-    else msm_launch_reduce_g2(c, buckets, g, s1, s2, wsum, d_out_wire, nred);
-    prof_end(c, P2B_PROF_MSM_REDUCE, 3);
-    c->launches += 3;
+    for (size_t set = 0; set < nsets; set++) {
+        const uint32_t *bk = set ? buckets_b : buckets;
+        uint32_t *out = j.d_out_wire + set * WU;
+        if constexpr (W == 8) msm_launch_reduce_g1(c, bk, g, s1, s2, wsum, out, nred);
+        else msm_launch_reduce_g2(c, bk, g, s1, s2, wsum, out, nred);
+        c->launches += 3;
+    }
+    prof_end(c, P2B_PROF_MSM_REDUCE, (int)(3 * nsets));
     P2B_CUDA(c, cudaGetLastError());
     return P2B_OK;
 }

@@ -33,7 +33,7 @@ struct Ctx {
     unsigned long long *d_err = nullptr;   // device error word
     unsigned long long *h_err = nullptr;   // pinned mirror
     // growable device scratch
-    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, fft_tw, gtable, gfft;
+    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, msm_f, fft_tw, gtable, gfft;
     // pinned staging rings + copy threads for pageable caller buffers (hostio.cu), created on first use
     HostIO *io = nullptr;
     cudaEvent_t ev[8] = {};

@@ -103,9 +103,9 @@ def sharded_msm(ctx, group_id, local_points, local_scalars, n_local, group=None,
     return ctx.sum_points(group_id, np.ascontiguousarray(parts).reshape(-1))
 
 
-def sharded_merge_pairs(ctx, v1, v2, rank, world, rng=None, scalar_bits=253, group=None, device=None):
+def sharded_merge_pairs(ctx, v1, v2, rank, world, rng=None, scalar_bits=253, group=None, device=None, flags=0):
     """merge_pairs (phase2/src/utils.rs:59-105) with the index range split across ranks: every rank combines its slice of
-    the two G1 vectors with its own random coefficients (two MSMs on its GPU); the ranks all-gather the 2 x 64-byte partial
+    the two G1 vectors with its own random coefficients (one pair-MSM pass on its GPU); the ranks all-gather the 2 x 64-byte partial
     results and each adds them up.  The random coefficients need not be shared: the check is a random linear combination
     per element either way.  Every rank returns the same (s, sx); a decode failure on one rank's shard raises on all."""
     from .powersoftau import _random_scalars, system_rng
@@ -118,9 +118,10 @@ def sharded_merge_pairs(ctx, v1, v2, rank, world, rng=None, scalar_bits=253, gro
     zero = bytes([0x40]) + bytes(63)
     part, err = zero + zero, None
     if hi > lo:
-        rho = _random_scalars(rng, hi - lo, scalar_bits)
+        _random_scalars(system_rng(), 0, scalar_bits)
         try:
-            part = ctx.msm(0, v1[lo * 64: hi * 64], rho) + ctx.msm(0, v2[lo * 64: hi * 64], rho)
+            a, b = ctx.msm_pair(0, v1[lo * 64: hi * 64], v2[lo * 64: hi * 64], None, bytes(rng.bytes(32)), scalar_bits, flags=flags)
+            part = a + b
         except _lib.P2BError as e:
             err = e
     parts = _gather_with_status(part, err, group=group, device=device).reshape(-1, 2, 64)

@@ -31,6 +31,7 @@ SYMBOLS = [
     "p2b_g1_sparse_mul", "p2b_g2_sparse_mul",
     "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
     "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants", "p2b_io_stats",
+    "p2b_g1_msm_pair", "p2b_g2_msm_pair", "p2b_g1_power_pairs", "p2b_g2_power_pairs", "p2b_random_scalars",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -78,6 +79,9 @@ def load():
             getattr(lib, "p2b_%s_msm" % g).argtypes = [vp, u8p, u8p, sz, u8p]
             getattr(lib, "p2b_%s_msm_dev" % g).argtypes = [vp, vp, vp, sz, u8p]
             getattr(lib, "p2b_%s_sum_points" % g).argtypes = [vp, u8p, sz, u8p]
+        getattr(lib, "p2b_%s_msm_pair" % g).argtypes = [vp, u8p, u8p, u8p, sz, u8p, u32, i32, i32, u8p, u8p]
+        getattr(lib, "p2b_%s_power_pairs" % g).argtypes = [vp, u8p, sz, u8p, u8p, u32, i32, i32, u8p, u8p]
+    lib.p2b_random_scalars.argtypes = [vp, u8p, u64, sz, u32, u8p]
     lib.p2b_sync.argtypes = [vp]
     lib.p2b_pot_accumulator_size.argtypes = [u32, i32]
     lib.p2b_pot_accumulator_size.restype = u64
@@ -311,6 +315,13 @@ class Context:
         self._check(fn(self.h, _ptr(pts), _ptr(out), n, in_enc, out_enc, flags))
         return out[: n * enc_size(group, out_enc)]
 
+    def validate(self, group, points, in_enc=ENC_UNCOMPRESSED, flags=CHECK_INPUT):
+        """Decode + check every point on the device without copying anything back (raises P2BError like recode)."""
+        pts = _host(points)
+        n = pts.size // enc_size(group, in_enc)
+        fn = self.lib.p2b_g2_recode if group == G2 else self.lib.p2b_g1_recode
+        self._check(fn(self.h, _ptr(pts), None, n, in_enc, ENC_UNCOMPRESSED, flags))
+
     def pot_decompress(self, response, challenge, size_log2, check_input=False, shard_index=0, shard_count=1):
         rs, ch = _host(response), challenge
         assert isinstance(ch, np.ndarray) and ch.dtype == np.uint8 and ch.flags.writeable
@@ -371,6 +382,49 @@ class Context:
         fn = self.lib.p2b_g2_msm if group == G2 else self.lib.p2b_g1_msm
         self._check(fn(self.h, _ptr(pts), _ptr(sc), n, _ptr(out)))
         return out.tobytes()
+
+    def msm_pair(self, group, points_a, points_b, scalars=None, seed=None, scalar_bits=0, in_enc=ENC_UNCOMPRESSED, flags=0):
+        """(sum k_i A_i, sum k_i B_i) in one pass (merge_pairs).  scalars=None: coefficients generated on the device from the
+        32-byte `seed` (ChaCha20 keystream), scalar_bits bits each."""
+        pa, pb = _host(points_a), _host(points_b)
+        size = enc_size(group, in_enc)
+        n = pa.size // size
+        if pa.size % size or pb.size != pa.size:
+            raise ValueError("msm_pair: the two point arrays must hold the same number of points")
+        sc = _host(scalars) if scalars is not None else None
+        if sc is not None and sc.size != 32 * n:
+            raise ValueError("msm_pair: need %d scalar bytes, got %d" % (32 * n, sc.size))
+        sd = _fixed(seed, 32, "seed") if seed is not None else None
+        full = enc_size(group, ENC_UNCOMPRESSED)
+        oa, ob = np.empty(full, dtype=np.uint8), np.empty(full, dtype=np.uint8)
+        fn = self.lib.p2b_g2_msm_pair if group == G2 else self.lib.p2b_g1_msm_pair
+        self._check(fn(self.h, _ptr(pa), _ptr(pb), _ptr(sc) if sc is not None else None, n, _ptr(sd) if sd is not None else None,
+                       scalar_bits, in_enc, flags, _ptr(oa), _ptr(ob)))
+        return oa.tobytes(), ob.tobytes()
+
+    def power_pairs(self, group, points, scalars=None, seed=None, scalar_bits=0, in_enc=ENC_UNCOMPRESSED, flags=0):
+        """merge_pairs(v[..n-1], v[1..]) over n points in one pass (power_pairs, powersoftau/src/utils.rs:133-135)."""
+        p = _host(points)
+        size = enc_size(group, in_enc)
+        n = p.size // size
+        if p.size % size or n < 1:
+            raise ValueError("power_pairs: need at least one point")
+        sc = _host(scalars) if scalars is not None else None
+        if sc is not None and sc.size != 32 * (n - 1):
+            raise ValueError("power_pairs: need %d scalar bytes, got %d" % (32 * (n - 1), sc.size))
+        sd = _fixed(seed, 32, "seed") if seed is not None else None
+        full = enc_size(group, ENC_UNCOMPRESSED)
+        oa, ob = np.empty(full, dtype=np.uint8), np.empty(full, dtype=np.uint8)
+        fn = self.lib.p2b_g2_power_pairs if group == G2 else self.lib.p2b_g1_power_pairs
+        self._check(fn(self.h, _ptr(p), n, _ptr(sc) if sc is not None else None, _ptr(sd) if sd is not None else None, scalar_bits,
+                       in_enc, flags, _ptr(oa), _ptr(ob)))
+        return oa.tobytes(), ob.tobytes()
+
+    def random_scalars(self, seed, n, scalar_bits=253, first=0):
+        """The coefficients the device generates for (seed, scalar_bits): n x 32 bytes big-endian."""
+        out = np.empty(max(1, 32 * n), dtype=np.uint8)
+        self._check(self.lib.p2b_random_scalars(self.h, _ptr(_fixed(seed, 32, "seed")), first, n, scalar_bits, _ptr(out)))
+        return out[: 32 * n]
 
     def sparse_mul(self, group, bases, row_offsets, cols, coeffs):
         """out[i] = sum_j coeffs[j] * bases[cols[j]] over CSR rows (the QAP evaluation of MPCParameters::new)."""

@@ -227,19 +227,18 @@ class VerificationError(Exception):
     """The `Err(())` of verify_contribution / MPCParameters::verify, with the failed check named."""
 
 
-def merge_pairs(ctx, v1, v2, rng=None, scalar_bits=253):
-    """Random linear combination (sum rho_i v1_i, sum rho_i v2_i) over G1 vectors (phase2/src/utils.rs:59-105): two MSMs.
+def merge_pairs(ctx, v1, v2, rng=None, scalar_bits=253, flags=0):
+    """Random linear combination (sum rho_i v1_i, sum rho_i v2_i) over G1 vectors (phase2/src/utils.rs:59-105) in one pass on
+    the GPU; the coefficients are generated on the device from 32 bytes of `rng` (the OS CSPRNG by default).
     `scalar_bits`: see powersoftau._random_scalars (253 = full-size scalars like the reference's Fr::rand)."""
-    from .powersoftau import _random_scalars, system_rng
-    rng = rng or system_rng()
+    from .powersoftau import merge_pairs as _merge
     n = v1.size // 64
     if n != v2.size // 64:
         raise ValueError("merge_pairs: length mismatch")
     if n == 0:
         zero = bytes([0x40]) + bytes(63)
         return zero, zero
-    rho = _random_scalars(rng, n, scalar_bits)
-    return ctx.msm(0, v1, rho), ctx.msm(0, v2, rho)
+    return _merge(ctx, 0, v1, v2, None, rng, scalar_bits, flags=flags)
 
 
 def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253, merge=None):
@@ -286,17 +285,20 @@ def verify_contribution(before, after, ctx=None, rng=None, scalar_bits=253, merg
         from .powersoftau import G2_ONE
         if not _lib.same_ratio((g1_one, delta_after), (G2_ONE, d2a)):
             fail("delta_g2 is inconsistent with delta_g1")
-        if merge is None or not (getattr(before, "validated", False) and getattr(after, "validated", False)):
-            ctx = ctx or _lib.Context(0)                                            # only the H / L checks need the GPU
+        # The MSM decodes its points unchecked unless asked.  The reference can only get here through
+        # MPCParameters::read(checked = true) (verify.rs); for objects built from raw bytes the curve check of H / L rides along
+        # in the same pass (P2B_CHECK_INPUT in the MSM's decode kernel).
+        unvalidated = not (getattr(before, "validated", False) and getattr(after, "validated", False))
         if merge is None:
-            merge = lambda a, b: merge_pairs(ctx, a, b, rng, scalar_bits)
-        # The MSM decodes its points unchecked.  The reference can only get here through MPCParameters::read(checked = true)
-        # (verify.rs); objects built from raw bytes are put through the checked codec first (curve membership of H / L).
-        for m, lay in ((before, lb), (after, la)):
-            if not getattr(m, "validated", False):
-                for name in ("h", "l"):
-                    if lay[name][1]:
-                        ctx.recode(0, raw(m, lay, name), _lib.ENC_UNCOMPRESSED, _lib.ENC_UNCOMPRESSED, _lib.CHECK_INPUT)
+            ctx = ctx or _lib.Context(0)                                            # only the H / L checks need the GPU
+            merge = lambda a, b: merge_pairs(ctx, a, b, rng, scalar_bits, _lib.CHECK_INPUT if unvalidated else 0)
+        elif unvalidated:
+            ctx = ctx or _lib.Context(0)
+            for m, lay in ((before, lb), (after, la)):
+                if not getattr(m, "validated", False):
+                    for name in ("h", "l"):
+                        if lay[name][1]:
+                            ctx.validate(0, raw(m, lay, name), _lib.ENC_UNCOMPRESSED, _lib.CHECK_INPUT)
         for name in ("h", "l"):                                                     # updated with delta^-1: ratios reversed
             if not _lib.same_ratio(merge(raw(before, lb, name), raw(after, la, name)), (d2a, d2b)):
                 fail("%s query was not multiplied by delta^-1" % name)

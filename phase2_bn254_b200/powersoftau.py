@@ -325,8 +325,7 @@ def verify_transformation(input_map, output_map, key, digest, input_is_compresse
     Returns True / False like the reference; a chunk that does not deserialize raises (the reference panics).
     `scalar_bits`: size of the random coefficients (see _random_scalars; 253 = the reference's full-size scalars)."""
     ctx = ctx or BatchedAccumulator.context()
-    rng = rng or system_rng()
-    _random_scalars(rng, 0, scalar_bits)                # refuse a too-small scalar_bits before any work
+    _random_scalars(system_rng(), 0, scalar_bits)       # refuse a too-small scalar_bits before any work
     assert len(digest) == 64
     p = parameters
     # The per-chunk same_ratio checks (two pairings each, ~35 ms on one core) run on host threads while the GPU works on
@@ -379,12 +378,40 @@ def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, i
     g1_pair = (pt(a_tau, 0, 64), pt(a_tau, 1, 64))
 
     pending = []
+    sec_in, sec_out = _sections(p, input_is_compressed), _sections(p, output_is_compressed)
+    enc_in = _lib.ENC_COMPRESSED if input_is_compressed else _lib.ENC_UNCOMPRESSED
+    enc_out = _lib.ENC_COMPRESSED if output_is_compressed else _lib.ENC_UNCOMPRESSED
+    fl_in = (_lib.CHECK_INPUT if check_input_for_correctness else 0) | _lib.REJECT_INFINITY
+    fl_out = (_lib.CHECK_INPUT if check_output_for_correctness else 0) | _lib.REJECT_INFINITY
 
-    def powers_ok(group, v, pair, wait=False):
-        n = v.size // (128 if group else 64)
-        if n < 2:
+    def chunk(amap, sec, name, start, count):
+        off, total, size, group = sec[name]
+        count = max(0, min(count, total - start))
+        return group, np.asarray(amap[off + start * size: off + (start + count) * size])
+
+    def check_before(name, start, count):
+        # the reference always deserializes the challenge chunk (read_chunk, :398-410): even with CheckForCorrectness::No a bad
+        # flag, a non-canonical coordinate or a point at infinity in `before` panics.  Validation only: nothing comes back.
+        group, raw = chunk(input_map, sec_in, name, start, count)
+        try:
+            ctx.validate(group, raw, enc_in, fl_in)
+        except _lib.P2BError as e:
+            BatchedAccumulator._raise(e)
+
+    def powers_ok(name, start, count, pair, wait=False, points=None):
+        """same_ratio(power_pairs(after.<name>[start .. start + count)), pair): the chunk goes to the GPU in its file encoding
+        (decompressed and checked there), the random coefficients are generated there, two points come back."""
+        if points is None:
+            group, raw = chunk(output_map, sec_out, name, start, count)
+            enc, fl = enc_out, fl_out
+        else:
+            group, raw, enc, fl = 0, points, _lib.ENC_UNCOMPRESSED, 0
+        if raw.size // _lib.enc_size(group, enc) < 2:
             return False                              # merge_pairs of nothing is (0, 0): same_ratio rejects zero
-        s, sx = power_pairs(ctx, group, v, _random_scalars(rng, n - 1, scalar_bits))
+        try:
+            s, sx = power_pairs(ctx, group, raw, None, rng, scalar_bits, enc, fl)
+        except _lib.P2BError as e:
+            BatchedAccumulator._raise(e)
         pending.append(pool.submit(same_ratio, (s, sx), pair) if group == 0 else pool.submit(same_ratio, pair, (s, sx)))
         done = [f for f in pending if f.done()]
         if wait:
@@ -397,54 +424,64 @@ def _verify_transformation(pool, ctx, rng, input_map, output_map, key, digest, i
         if end == start:
             raise RuntimeError("Chunk does not have a min and max")            # the reference's panic (:462)
         size = end - start + 1 + (0 if end == p.powers_length - 1 else 1)      # one extra element: chunks overlap
-        # the reference always deserializes the challenge chunk (read_chunk, :404-410): even with CheckForCorrectness::No a
-        # bad flag, a non-canonical coordinate or a point at infinity in `before` panics
         for name in ("tau_g1", "tau_g2", "alpha_g1", "beta_g1"):
-            before(name, start, size)
-        v = after("tau_g1", start, size)
-        if not powers_ok(0, v, g2_pair):
+            check_before(name, start, size)
+        if not powers_ok("tau_g1", start, size, g2_pair):
             return False
-        if not powers_ok(1, after("tau_g2", start, size), g1_pair):
+        if not powers_ok("tau_g2", start, size, g1_pair):
             return False
-        if not powers_ok(0, after("alpha_g1", start, size), g2_pair):
+        if not powers_ok("alpha_g1", start, size, g2_pair):
             return False
-        if not powers_ok(0, after("beta_g1", start, size), g2_pair):
+        if not powers_ok("beta_g1", start, size, g2_pair):
             return False
         if end == p.powers_length - 1:
-            last_first[0] = pt(v, size - 1, 64)
+            last_first[0] = pt(after("tau_g1", end, 1), 0, 64)
     for start in range(p.powers_length, p.powers_g1_length, p.batch_size):
         end = min(start + p.batch_size, p.powers_g1_length) - 1
         if end == start:
             raise RuntimeError("Chunk does not have a min and max")            # (:526)
         size = end - start + 1 + (0 if end == p.powers_g1_length - 1 else 1)
-        before("tau_g1", start, size)
-        v = after("tau_g1", start, size)
-        if not powers_ok(0, v, g2_pair):
+        check_before("tau_g1", start, size)
+        if not powers_ok("tau_g1", start, size, g2_pair):
             return False
         if start == p.powers_length:
-            last_first[1] = pt(v, 0, 64)
+            last_first[1] = pt(after("tau_g1", start, 1), 0, 64)
     if last_first[0] is None or last_first[1] is None:
         return False
-    return powers_ok(0, np.frombuffer(last_first[0] + last_first[1], dtype=np.uint8), g2_pair, wait=True)
+    return powers_ok(None, 0, 0, g2_pair, wait=True, points=np.frombuffer(last_first[0] + last_first[1], dtype=np.uint8))
 
 
 BatchedAccumulator.verify_transformation = staticmethod(verify_transformation)
 
 
-def merge_pairs(ctx, group, v1, v2, scalars):
+def _seed(rng):
+    """32 bytes for the device-side coefficient generator (ChaCha20 keyed by them) from `rng` (system_rng by default)."""
+    return bytes((rng or system_rng()).bytes(32))
+
+
+def merge_pairs(ctx, group, v1, v2, scalars=None, rng=None, scalar_bits=253, in_enc=_lib.ENC_UNCOMPRESSED, flags=0):
     """(sum r_i v1_i, sum r_i v2_i): the random linear combination behind every same_ratio check of the verifier
-    (powersoftau/src/utils.rs:112-130, phase2/src/utils.rs:59-105); two Pippenger MSMs on the GPU.  The reference draws
-    the r_i from thread_rng; here they are explicit (32-byte big-endian each).  Returns two uncompressed points."""
-    return ctx.msm(group, v1, scalars), ctx.msm(group, v2, scalars)
+    (powersoftau/src/utils.rs:112-130, phase2/src/utils.rs:59-105) in ONE pass on the GPU (p2b_g{1,2}_msm_pair: one sort of the
+    shared coefficients, two bucket sets).  The reference draws the r_i from thread_rng; here they are either explicit
+    (`scalars`, 32-byte big-endian each) or generated on the device from 32 bytes of `rng` (the OS CSPRNG by default).
+    Returns two uncompressed points."""
+    if scalars is not None:
+        return ctx.msm_pair(group, v1, v2, scalars, in_enc=in_enc, flags=flags)
+    _random_scalars(system_rng(), 0, scalar_bits)
+    return ctx.msm_pair(group, v1, v2, None, _seed(rng), scalar_bits, in_enc, flags)
 
 
-def power_pairs(ctx, group, v, scalars):
-    """merge_pairs(v[..n-1], v[1..]) (utils.rs:133-135): checks that consecutive elements have the same ratio."""
-    size = 128 if group else 64
-    a = np.frombuffer(v, dtype=np.uint8) if not isinstance(v, np.ndarray) else v
-    n = a.size // size
-    sc = np.frombuffer(scalars, dtype=np.uint8) if not isinstance(scalars, np.ndarray) else scalars
-    return merge_pairs(ctx, group, a[: (n - 1) * size], a[size:], sc[: (n - 1) * 32])
+def power_pairs(ctx, group, v, scalars=None, rng=None, scalar_bits=253, in_enc=_lib.ENC_UNCOMPRESSED, flags=0):
+    """merge_pairs(v[..n-1], v[1..]) (utils.rs:133-135): checks that consecutive elements have the same ratio.  One upload of
+    v, one pass (p2b_g{1,2}_power_pairs)."""
+    if scalars is not None:
+        size = _lib.enc_size(group, in_enc)
+        a = np.frombuffer(v, dtype=np.uint8) if not isinstance(v, np.ndarray) else v
+        n = a.size // size
+        sc = np.frombuffer(scalars, dtype=np.uint8) if not isinstance(scalars, np.ndarray) else scalars
+        return ctx.power_pairs(group, a, sc[: (n - 1) * 32], in_enc=in_enc, flags=flags)
+    _random_scalars(system_rng(), 0, scalar_bits)
+    return ctx.power_pairs(group, v, None, _seed(rng), scalar_bits, in_enc, flags)
 
 
 def prepare_phase2(ctx, accumulator_map, parameters, m, input_is_compressed=True, check_input_for_correctness=True,

@@ -9,31 +9,9 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class OracleCtx:
-    """Duck-typed stand-in for lib.Context in a GPU-less test: same msm / sum_points contract, CPU oracle inside."""
-
-    def __init__(self, oc):
-        self.oc = oc
-
-    def msm(self, group, points, scalars):
-        from phase2_bn254_b200 import lib
-        try:
-            return self.oc.msm(group, bytes(points), bytes(scalars), threads=2)
-        except self.oc.OracleError as e:
-            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
-
-    def sum_points(self, group, points):
-        return self.oc.sum_points(group, bytes(points))
-
-    def recode(self, group, points, in_enc, out_enc, flags=0, out=None):
-        from phase2_bn254_b200 import lib
-        import numpy as np
-        try:
-            res = self.oc.batch_mul(group, bytes(np.asarray(points)), (1).to_bytes(32, "big"), in_enc, out_enc,
-                                    bool(flags & lib.CHECK_INPUT), bool(flags & lib.REJECT_INFINITY), threads=2)
-        except self.oc.OracleError as e:
-            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
-        return np.frombuffer(res, dtype=np.uint8)
+def OracleCtx(oc):
+    from util import OracleCtx as C
+    return C(oc, threads=2)
 
 
 def _worker(rank, world, port, q):

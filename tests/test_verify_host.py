@@ -11,23 +11,11 @@ import pytest
 from util import G1_GEN, G2_GEN, R_MOD, be
 
 
-class OracleCtx:
-    """The three Context calls the mirrors make, answered by the CPU oracle."""
+from util import OracleCtx as _OracleCtx
 
-    def __init__(self, oracle):
-        self.oc = oracle
 
-    def msm(self, group, points, scalars):
-        return self.oc.msm(group, bytes(np.asarray(points)), bytes(np.asarray(scalars)), threads=4)
-
-    def recode(self, group, points, in_enc, out_enc, flags=0, out=None):
-        from phase2_bn254_b200 import lib
-        try:
-            res = self.oc.batch_mul(group, bytes(np.asarray(points)), be(1), in_enc, out_enc, bool(flags & lib.CHECK_INPUT),
-                                    bool(flags & lib.REJECT_INFINITY), threads=4)
-        except self.oc.OracleError as e:
-            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
-        return np.frombuffer(res, dtype=np.uint8)
+class OracleCtx(_OracleCtx):
+    pass
 
 
 @pytest.fixture(scope="module")

@@ -31,3 +31,89 @@ def random_points(oc, group, n, seed, threads=8):
 def random_scalars(n, seed):
     rng = random.Random(seed)
     return b"".join(be(rng.randrange(R_MOD)) for _ in range(n))
+
+
+# ---- ChaCha20 (RFC 7539 block function) in python: the reference for the coefficients the library generates on the device
+def _rotl(v, k):
+    return ((v << k) | (v >> (32 - k))) & 0xffffffff
+
+
+def chacha20_block(key_words, w12, w13, w14, w15):
+    """64 keystream bytes for the given key (8 little-endian words) and the last four state words."""
+    st = [0x61707865, 0x3320646e, 0x79622d32, 0x6b206574] + list(key_words) + [w12, w13, w14, w15]
+    x = list(st)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xffffffff; x[d] = _rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & 0xffffffff; x[b] = _rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & 0xffffffff; x[d] = _rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & 0xffffffff; x[b] = _rotl(x[b] ^ x[c], 7)
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return b"".join(((a + b) & 0xffffffff).to_bytes(4, "little") for a, b in zip(x, st))
+
+
+def device_scalars(seed, n, bits=253, first=0):
+    """What p2b_random_scalars / the seed-driven msm_pair use (include/p2b.h): coefficient i = keystream bytes
+    [32 i, 32 i + 32) -- block counter i // 2 in words 12-13 -- as a big-endian integer, cleared above `bits` bits."""
+    key = [int.from_bytes(seed[4 * i: 4 * i + 4], "little") for i in range(8)]
+    out = bytearray()
+    blocks = {}
+    for i in range(first, first + n):
+        b = i // 2
+        if b not in blocks:
+            blocks[b] = chacha20_block(key, b & 0xffffffff, b >> 32, 0, 0)
+        v = int.from_bytes(blocks[b][32 * (i % 2): 32 * (i % 2) + 32], "big") & ((1 << bits) - 1)
+        out += v.to_bytes(32, "big")
+    return bytes(out)
+
+
+class OracleCtx:
+    """Duck-typed stand-in for lib.Context in GPU-less tests of the host-side mirrors: the Context calls they make, answered
+    by the CPU oracle (and, for the device-generated verifier coefficients, by the python ChaCha20 above)."""
+
+    def __init__(self, oc, threads=4):
+        self.oc, self.threads = oc, threads
+
+    def _wrap(self, fn, *a, **k):
+        from phase2_bn254_b200 import lib
+        try:
+            return fn(*a, **k)
+        except self.oc.OracleError as e:
+            raise lib.P2BError(e.code, "oracle", e.index, e.sub)
+
+    def msm(self, group, points, scalars):
+        import numpy as np
+        return self._wrap(self.oc.msm, group, bytes(np.asarray(points)), bytes(np.asarray(scalars)), threads=self.threads)
+
+    def sum_points(self, group, points):
+        return self.oc.sum_points(group, bytes(points))
+
+    def recode(self, group, points, in_enc, out_enc, flags=0, out=None):
+        import numpy as np
+        from phase2_bn254_b200 import lib
+        res = self._wrap(self.oc.batch_mul, group, bytes(np.asarray(points)), be(1), in_enc, out_enc, bool(flags & lib.CHECK_INPUT),
+                         bool(flags & lib.REJECT_INFINITY), threads=self.threads)
+        return np.frombuffer(res, dtype=np.uint8)
+
+    def validate(self, group, points, in_enc=0, flags=1):
+        self.recode(group, points, in_enc, 0, flags)
+
+    def _coeffs(self, n, scalars, seed, bits):
+        import numpy as np
+        return bytes(np.asarray(scalars)) if scalars is not None else device_scalars(bytes(seed), n, bits)
+
+    def msm_pair(self, group, points_a, points_b, scalars=None, seed=None, scalar_bits=0, in_enc=0, flags=0):
+        a = self.recode(group, points_a, in_enc, 0, flags).tobytes()
+        b = self.recode(group, points_b, in_enc, 0, flags).tobytes()
+        k = self._coeffs(len(a) // (128 if group else 64), scalars, seed, scalar_bits)
+        return self.msm(group, a, k), self.msm(group, b, k)
+
+    def power_pairs(self, group, points, scalars=None, seed=None, scalar_bits=0, in_enc=0, flags=0):
+        size = 128 if group else 64
+        v = self.recode(group, points, in_enc, 0, flags).tobytes()
+        n = len(v) // size
+        k = self._coeffs(n - 1, scalars, seed, scalar_bits)
+        return self.msm(group, v[: (n - 1) * size], k), self.msm(group, v[size:], k)
