@@ -239,6 +239,243 @@ def pageable_msm(args, torch, np, ctx, np_pts, np_sc, m):
     return out
 
 
+def scaling_extras(args, torch, np, dist, pdist, lib, ctx, rank, world, device, e2e_ms, n_headline):
+    """Multi-GPU rows (BASELINE config 5, the sharded transform / contribute, the north-star contribute at 2^26 constraints) and
+    the host-side ceiling that explains the end-to-end scaling.  Run by every rank; returns the record on rank 0.
+    Wall-clock between barriers, max over ranks, for the host-buffer paths; shared files live in --mmap-dir (/dev/shm)."""
+    import hashlib
+    import shutil
+    import struct
+    import tempfile
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_floats(v):
+        if world == 1:
+            return [float(v)]
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        o = torch.empty(world, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(o, t)
+        return [float(x) for x in o.cpu()]
+
+    def bcast(obj):
+        if world == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def wall(fn, reps=1):
+        best = 1e30
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            best = min(best, max_over_ranks(time.perf_counter() - t0))
+        return best
+
+    # -- (1) raw concurrent pinned host -> device bandwidth of this box, all ranks at once: the ceiling of every e2e number
+    nb = 1 << 30
+    hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    hbuf.zero_()
+    dbuf = torch.empty(nb, dtype=torch.uint8, device=device)
+    dbuf.copy_(hbuf, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        dbuf.copy_(hbuf, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    per_rank = gather_floats(4 * nb / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del hbuf, dbuf
+    need = 96.0 * n_headline / (e2e_ms * 1e-3) / 1e9
+    out["h2d_ceiling"] = {"pinned_GBps_per_rank_concurrent": [round(x, 1) for x in per_rank], "aggregate_GBps": round(sum(per_rank), 1),
+                          "e2e_msm_GBps_per_rank_achieved": round(need, 1),
+                          "note": "every rank copies 4 x 1 GiB pinned -> device at the same time (CUDA events); the e2e MSM moves 96 B per "
+                                  "term per step from pinned host memory on every rank at once"}
+
+    # -- (2) BASELINE config 5: G1 + G2 Pippenger, 2^25 terms per GPU (2^28 in total on 8 GPUs), point-range shards, all-gather of
+    #        the per-rank results + local sum; device-resident
+    lg5 = args.config5_log_n
+    n5 = 1 << lg5
+    sc5 = make_scalars(torch, n5, 0x5dbe6259 + rank, device)
+    res5 = {}
+    for grp, name in ((0, "g1"), (1, "g2")):
+        p5 = make_points(torch, np, ctx, grp, n5, 1 + rank * n5, device)
+        box = {}
+
+        def step():
+            box["r"] = pdist.sharded_msm(ctx, grp, p5.data_ptr(), sc5.data_ptr(), n5, device=device, on_device=True) if world > 1 \
+                else ctx.msm_dev(grp, p5.data_ptr(), sc5.data_ptr(), n5)
+
+        step()
+        t = wall(step, 3)
+        part = ctx.msm_dev(grp, p5.data_ptr(), sc5.data_ptr(), n5)
+        parts = pdist.all_gather_bytes(part, device=device) if world > 1 else part
+        res5[name] = {"ms": round(t * 1e3, 3), "Mscalar_mul_per_s": round(world * n5 / t / 1e6, 1),
+                      "equals_sum_of_per_rank_results": bool(ctx.sum_points(grp, np.frombuffer(parts, dtype=np.uint8)) == box["r"]),
+                      "result_prefix": box["r"][:16].hex()}
+        # cross-check at 2^20 terms per rank: the sharded sum equals ONE GPU's MSM over all world * 2^20 terms (rank 0 regenerates them)
+        m = 1 << 20
+        small = pdist.sharded_msm(ctx, grp, p5.data_ptr(), sc5.data_ptr(), m, device=device, on_device=True) if world > 1 \
+            else ctx.msm_dev(grp, p5.data_ptr(), sc5.data_ptr(), m)
+        if world > 1:                        # every rank's first 2^20 points and scalars, gathered over NCCL
+            esz = 128 if grp else 64
+            allp = torch.empty(world * m * esz, dtype=torch.uint8, device=device)
+            alls = torch.empty(world * m * 32, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allp, p5[: m * esz].contiguous())
+            dist.all_gather_into_tensor(alls, sc5[: m * 32].contiguous())
+            torch.cuda.synchronize()
+            if rank == 0:
+                res5[name]["sharded_equals_single_gpu_at_2^20_per_rank"] = bool(
+                    ctx.msm_dev(grp, allp.data_ptr(), alls.data_ptr(), world * m) == small)
+            del allp, alls
+        del p5
+        torch.cuda.empty_cache()
+    del sc5
+    out["config5_g1_g2_msm_2^%d_per_gpu" % lg5] = dict(res5, total_terms_per_group=world * n5,
+                                                        combined_ms=round(res5["g1"]["ms"] + res5["g2"]["ms"], 3))
+
+    # -- shared files for the sharded host-buffer rows
+    base = args.mmap_dir or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    d = bcast(tempfile.mkdtemp(prefix="p2b_scale_", dir=base) if rank == 0 else None)
+    free_gb = shutil.disk_usage(d).free / 1e9
+    try:
+        # -- (3) BatchedAccumulator::transform at 2^22 powers, every section split across the ranks, disjoint writes into ONE
+        #        response file; the bytes must equal the single-GPU response
+        size = args.sharded_transform_size
+        prm = CeremonyParams(size, 256)
+        key = PrivateKey(TAU, 0x2222 * 2**190 % R_MOD, 0x3333 * 2**180 % R_MOD)
+        cf, rf, rf1 = os.path.join(d, "challenge"), os.path.join(d, "response"), os.path.join(d, "response_n1")
+        if rank == 0:
+            ch = np.memmap(cf, dtype=np.uint8, mode="w+", shape=(prm.accumulator_size,))
+            ch[:64] = np.frombuffer(hashlib.blake2b(b"").digest(), dtype=np.uint8)
+            BatchedAccumulator.generate_initial(ch, False, prm)
+            ch.flush()
+            del ch
+            for f in (rf, rf1):
+                with open(f, "wb") as fh:
+                    fh.truncate(prm.contribution_size)
+        barrier()
+        cm = np.memmap(cf, dtype=np.uint8, mode="r")
+        rm = np.memmap(rf, dtype=np.uint8, mode="r+")
+        # warm-up on a 2^10 accumulator: module load of the batch_exp kernels and the pinned staging rings of this context
+        p10 = CeremonyParams(10, 256)
+        w_in = np.zeros(p10.accumulator_size, dtype=np.uint8)
+        BatchedAccumulator.generate_initial(w_in, False, p10)
+        BatchedAccumulator.transform(w_in, np.zeros(p10.contribution_size, dtype=np.uint8), False, True, False, key, p10, ctx=ctx)
+        t = wall(lambda: pdist.sharded_transform(ctx, cm, rm, prm, key, rank, world), 2)
+        rm.flush()
+        barrier()
+        row = {"wall_s": round(t, 4), "ranks": world, "challenge_bytes": prm.accumulator_size}
+        if rank == 0:
+            end = prm.contribution_size - prm.public_key_size
+            body = np.memmap(rf, dtype=np.uint8, mode="r")[64:end]
+            row["response_body_blake2b"] = hashlib.blake2b(body).hexdigest()[:32]
+            if world > 1:
+                r1 = np.memmap(rf1, dtype=np.uint8, mode="r+")
+                t0 = time.perf_counter()
+                BatchedAccumulator.transform(cm, r1, False, True, False, key, prm, ctx=ctx)
+                row["single_gpu_wall_s"] = round(time.perf_counter() - t0, 4)
+                row["equals_single_gpu_response"] = bool(np.array_equal(r1[64:end], body))
+                del r1
+            del body
+        out["sharded_transform_2^%d" % size] = row
+        del cm, rm
+        barrier()
+        if rank == 0:
+            for f in (cf, rf, rf1):
+                os.remove(f)
+
+        # -- (4) MPCParameters::contribute with H and L split across the ranks: 2^24 constraints, and the north-star size 2^26
+        #        (2^27 H / L points, 8.6 GB of parameters each way) when the shared directory has room for the files
+        delta = np.frombuffer(be(0x2b5d1c3e7f9a0b4c6d8e0f1a2b3c4d5e6f708192a3b4c5d6e7f8091a2b3c4d5e % R_MOD), dtype=np.uint8)
+        for lgm in (24, 26):
+            m = 1 << lgm
+            nh, nl = m - 1, m
+            total = 64 * 2 + 128 * 2 + 64 + 128 + 4 + 128 + 4 + nh * 64 + 4 + nl * 64 + (4 + 1024) * 2 + 4 + 2048 + 64 + 4
+            if lgm > args.max_contribute_log or free_gb < 3.2 * total / 1e9 + 2:
+                out["sharded_contribute_2^%d" % lgm] = {"skipped": "needs %.1f GB in %s (free: %.1f GB) or above --max-contribute-log"
+                                                                   % (3.2 * total / 1e9, base, free_gb)}
+                continue
+            pf, of, of1 = os.path.join(d, "params"), os.path.join(d, "params_out"), os.path.join(d, "params_out_n1")
+            if rank == 0:
+                ptsd = make_points(torch, np, ctx, 0, m, 1, device)
+                g1 = ptsd[: 64 * 16].cpu().numpy().tobytes()
+                head = (g1[0:64] + g1[64:128] + G2_GEN + G2_GEN + G1_GEN + G2_GEN + struct.pack(">I", 2) + g1[128:256] +
+                        struct.pack(">I", nh))
+                tail = (struct.pack(">I", 16) + g1[:1024] + struct.pack(">I", 16) + g1[:1024] + struct.pack(">I", 16) + G2_GEN * 16 +
+                        hashlib.blake2b(b"scale").digest() + struct.pack(">I", 0))
+                assert len(head) + nh * 64 + 4 + nl * 64 + len(tail) == total
+                pm = np.memmap(pf, dtype=np.uint8, mode="w+", shape=(total,))
+                hp = ptsd.cpu().numpy()
+                o = 0
+                pm[o:o + len(head)] = np.frombuffer(head, dtype=np.uint8); o += len(head)
+                pm[o:o + nh * 64] = hp[: nh * 64]; o += nh * 64
+                pm[o:o + 4] = np.frombuffer(struct.pack(">I", nl), dtype=np.uint8); o += 4
+                pm[o:o + nl * 64] = hp[: nl * 64]; o += nl * 64
+                pm[o:o + len(tail)] = np.frombuffer(tail, dtype=np.uint8)
+                pm.flush()
+                s_g1 = np.frombuffer(g1[5 * 64: 6 * 64], dtype=np.uint8).copy()
+                r_g2 = np.frombuffer(lib.hash_to_g2(ctx.phase2_transcript(pm, delta, s_g1)), dtype=np.uint8).copy()
+                del pm, hp, ptsd
+                torch.cuda.empty_cache()
+                for f in (of,) + ((of1,) if world > 1 else ()):
+                    with open(f, "wb") as fh:
+                        fh.truncate(total + 384)
+                keys = (s_g1.tobytes(), r_g2.tobytes())
+            else:
+                keys = None
+            keys = bcast(keys)
+            s_g1, r_g2 = np.frombuffer(keys[0], dtype=np.uint8), np.frombuffer(keys[1], dtype=np.uint8)
+            barrier()
+            pm = np.memmap(pf, dtype=np.uint8, mode="r")
+            om = np.memmap(of, dtype=np.uint8, mode="r+")
+            box = {}
+
+            def step():
+                box["h"] = pdist.sharded_contribute(ctx, pm, om, delta, s_g1, r_g2, rank, world)
+
+            t = wall(step, 2)
+            row = {"wall_s": round(t, 4), "ranks": world, "points": nh + nl, "params_bytes": total,
+                   "Mpoints_per_s": round((nh + nl) / t / 1e6, 1), "contribution_hash": box["h"].hex()[:32],
+                   "buffers": "memory maps of files in %s (pageable; staged through pinned rings)" % base}
+            if rank == 0 and world > 1:
+                o1 = np.memmap(of1, dtype=np.uint8, mode="r+")
+                t0 = time.perf_counter()
+                _, h1 = ctx.phase2_contribute(pm, delta, s_g1, r_g2, out=o1)
+                row["single_gpu_wall_s"] = round(time.perf_counter() - t0, 4)
+                row["equals_single_gpu_file"] = bool(h1 == box["h"] and np.array_equal(o1, np.memmap(of, dtype=np.uint8, mode="r")))
+                del o1
+            out["sharded_contribute_2^%d" % lgm] = row
+            del pm, om
+            barrier()
+            if rank == 0:
+                for f in (pf, of, of1):
+                    if os.path.exists(f):
+                        os.remove(f)
+    finally:
+        barrier()
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+    return out if rank == 0 else None
+
+
 def timed(torch, stream, fn, reps):
     """fn() `reps` times between two CUDA events on the library's stream; returns (device ms, wall ms) per rep."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -364,6 +601,15 @@ def run_ours(args, rank, world, local_rank):
         pageable = pageable_msm(args, torch, np, ctx, np_pts, np_sc, min(n, 1 << 24))
     del h_pts, h_sc, np_pts, np_sc
 
+    # ---- rows that only exist with several GPUs, or whose single-GPU figure is the reference point for them (all ranks take
+    #      part; rank 0 keeps the record)
+    scale_rows = None
+    if not args.no_extras:
+        del pts, sc
+        torch.cuda.empty_cache()
+        pts = sc = None
+        scale_rows = scaling_extras(args, torch, np, dist, pdist, lib, ctx, rank, world, device, e2e_ms, n)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -415,8 +661,12 @@ def run_ours(args, rank, world, local_rank):
         line["e2e"]["pageable_caller_buffers_msm_2^%d" % (pageable["terms"].bit_length() - 1)] = pageable
     clocks.stop()
 
+    if scale_rows:
+        line["scaling_rows"] = scale_rows
     if world == 1:
         if not args.no_extras:
+            pts = make_points(torch, np, ctx, 0, 1 << 22, 1, device)
+            sc = make_scalars(torch, 1 << 22, 0x8d313d76, device)
             line["extras"] = extras(args, torch, np, ctx, stream, device, lib, pts, sc)
         del pts, sc
         torch.cuda.empty_cache()
@@ -653,6 +903,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--mmap-dir", default=None, help="directory for the memory-mapped input files of the pageable-buffer extras")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config5-log-n", type=int, default=25, help="scaling rows: log2 of the G1 / G2 MSM terms per GPU (config 5)")
+    ap.add_argument("--sharded-transform-size", type=int, default=22, help="scaling rows: log2 of the powers of the sharded transform")
+    ap.add_argument("--max-contribute-log", type=int, default=26, help="scaling rows: largest log2(constraints) of the sharded contribute")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

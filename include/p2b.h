@@ -158,6 +158,14 @@ int p2b_phase2_contribute(p2b_ctx *ctx, const uint8_t *params, uint64_t params_l
                           uint64_t params_out_len, const uint8_t delta_be[32], const uint8_t s_g1[64],
                           const uint8_t r_g2[128], uint8_t hash_out[64]);
 
+/* The same with H and L split into `shard_count` contiguous ranges: rank `shard_index` rewrites only its range of both vectors
+ * in params_out (shared storage, e.g. the output file mapped by every rank; no collective, disjoint bytes -- the static range
+ * split of the reference's thread chunks, parameters.rs:430-438, applied to GPUs); shard 0 also writes every other byte.  All
+ * shards return the same hash. */
+int p2b_phase2_contribute_sharded(p2b_ctx *ctx, const uint8_t *params, uint64_t params_len, uint8_t *params_out,
+                                  uint64_t params_out_len, const uint8_t delta_be[32], const uint8_t s_g1[64],
+                                  const uint8_t r_g2[128], uint8_t hash_out[64], uint32_t shard_index, uint32_t shard_count);
+
 /* ---- Pippenger MSM ---- */
 /* out = sum scalars[i] * points[i]; points uncompressed wire, out uncompressed wire (64 / 128 B). */
 int p2b_g1_msm(p2b_ctx *ctx, const uint8_t *points, const uint8_t *scalars_be32, size_t n, uint8_t *out);

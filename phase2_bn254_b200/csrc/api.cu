@@ -382,9 +382,15 @@ static int phase2_transcript(Ctx *c, const uint8_t *params, uint64_t len, const 
     return P2B_OK;
 }
 
+// shard_index / shard_count: the H and L vectors are split into contiguous ranges (one per rank / GPU, no collective: every rank
+// writes a disjoint byte range of the shared output); shard 0 also writes everything else (header, the other vectors, the
+// new delta_g1 / delta_g2, the appended public key) and is the one whose hash_out is meaningful for the file -- the hash is
+// computed on every shard from the same inputs, so all ranks return the same 64 bytes.
 static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_t *out, uint64_t out_len, const uint8_t *delta,
-                             const uint8_t *s, const uint8_t *r_g2, uint8_t hash_out[64]) {
+                             const uint8_t *s, const uint8_t *r_g2, uint8_t hash_out[64], uint32_t shard_index = 0,
+                             uint32_t shard_count = 1) {
     if (!params || !out || !delta || !s || !r_g2 || !hash_out) return ctx_fail(c, P2B_EARG, "null argument");
+    if (shard_count == 0 || shard_index >= shard_count) return ctx_fail(c, P2B_EARG, "bad shard");
     ParamsLayout L;
     int rc = params_layout(c, params, len, L);
     if (rc) return rc;
@@ -414,7 +420,9 @@ static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_
     for (int v = 0; v < 2; v++) {
         HostJob j;
         memset(&j, 0, sizeof j);
-        j.g2 = 0; j.in = params + vecs[v].off; j.out = out + vecs[v].off; j.n = vecs[v].n;
+        uint64_t lo, hi;
+        shard_range(vecs[v].n, shard_index, shard_count, lo, hi);
+        j.g2 = 0; j.in = params + vecs[v].off + lo * 64; j.out = out + vecs[v].off + lo * 64; j.n = hi - lo;
         j.in_enc = P2B_ENC_UNCOMPRESSED; j.out_enc = P2B_ENC_UNCOMPRESSED; j.flags = 0;
         j.sc.mode = 1;
         memcpy(j.sc.k, dinv.l, 32);
@@ -433,7 +441,7 @@ static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_
         if ((rc = run_host_job(c, j))) return rc;
     }
     // everything that does not change is copied through while the GPU works (h and l are rewritten by the jobs above)
-    if (out != params) {
+    if (out != params && shard_index == 0) {
         const uint64_t h_end = L.h_off + L.h_n * 64, l_end = L.l_off + L.l_n * 64;
         memcpy(out, params, L.h_off);
         memcpy(out + h_end, params + h_end, L.l_off - h_end);
@@ -452,12 +460,14 @@ static int phase2_contribute(Ctx *c, const uint8_t *params, uint64_t len, uint8_
         h.update(pk_s_delta, 64);
         h.finish(pk_transcript);
     }
-    // vk.delta_g1 / vk.delta_g2 *= delta (parameters.rs:507-508)
-    memcpy(out + L.delta_g1, pk_delta_after, 64);
-    memcpy(out + L.delta_g2, g2_out + 128, 128);
-    // contributions.push(pubkey)
-    wr_u32be(out + L.contrib_count_off, (uint32_t)(L.contrib_n + 1));
-    memcpy(out + len, pubkey, 384);
+    if (shard_index == 0) {
+        // vk.delta_g1 / vk.delta_g2 *= delta (parameters.rs:507-508)
+        memcpy(out + L.delta_g1, pk_delta_after, 64);
+        memcpy(out + L.delta_g2, g2_out + 128, 128);
+        // contributions.push(pubkey)
+        wr_u32be(out + L.contrib_count_off, (uint32_t)(L.contrib_n + 1));
+        memcpy(out + len, pubkey, 384);
+    }
     Blake2b::hash(pubkey, 384, hash_out);
     return P2B_OK;
 }
@@ -621,6 +631,12 @@ int p2b_phase2_transcript(p2b_ctx *h, const uint8_t *params, uint64_t params_len
 int p2b_phase2_contribute(p2b_ctx *h, const uint8_t *params, uint64_t params_len, uint8_t *params_out, uint64_t params_out_len,
                           const uint8_t delta[32], const uint8_t s[64], const uint8_t r[128], uint8_t hash_out[64]) {
     return h ? phase2_contribute(&h->c, params, params_len, params_out, params_out_len, delta, s, r, hash_out) : P2B_EARG;
+}
+int p2b_phase2_contribute_sharded(p2b_ctx *h, const uint8_t *params, uint64_t params_len, uint8_t *params_out, uint64_t params_out_len,
+                                  const uint8_t delta[32], const uint8_t s[64], const uint8_t r[128], uint8_t hash_out[64],
+                                  uint32_t shard_index, uint32_t shard_count) {
+    return h ? phase2_contribute(&h->c, params, params_len, params_out, params_out_len, delta, s, r, hash_out, shard_index, shard_count)
+             : P2B_EARG;
 }
 
 }  // extern "C"

@@ -5,10 +5,12 @@
 // file-backed memory.  cudaMemcpyAsync from such memory is staged by the driver on the calling thread (one thread,
 // synchronous), which serialises the three-stream pipelines of this library.  Here:
 //   * a buffer that is already page-locked (cudaHostAlloc / cudaHostRegister) is copied directly, asynchronously;
-//   * a pageable source is copied by a small pool of host threads into a ring of pinned slots, each slot then goes to the
-//     device with cudaMemcpyAsync on the caller's stream (the next slot is being filled while the previous one is in flight);
-//   * a pageable destination receives its bytes from a ring of pinned slots that a drain thread empties as the D2H events
-//     complete, so the thread that queues GPU work never waits for a device -> pageable copy.
+//   * a pageable source is cut into 8 MiB pieces that a pool of host threads copies into their own pinned slots (two per
+//     thread: one being filled while the other is in flight); each thread issues its piece's cudaMemcpyAsync on the caller's
+//     stream itself, and the call returns once every piece has been issued;
+//   * a pageable destination receives its bytes from a ring of pinned slots that the same threads empty as the D2H events
+//     complete (several at a time: the first touch of a fresh output mapping is page-fault bound), so the thread that queues
+//     GPU work never waits for a device -> pageable copy.
 // cudaHostRegister on the caller's range is not used: page-locking costs about as much per byte as the copy itself, it is
 // paid before the first byte moves, and it is refused for some file-backed mappings.
 #include <algorithm>
@@ -25,90 +27,68 @@ namespace p2b {
 
 struct HostIO {
     static constexpr size_t SLOT = (size_t)8 << 20;
-    static constexpr int NIN = 6, NOUT = 12;
+    static constexpr int MAXT = 16, NOUT = 16;
     struct Slot { char *buf = nullptr; cudaEvent_t ev = nullptr; };
-    Slot in[NIN], out[NOUT];
-    int next_in = 0, next_out = 0;
+    // H2D: every worker owns two pinned slots (fill one while the other is in flight); D2H: a shared ring the queueing thread
+    // hands out and the workers empty
+    Slot in[MAXT][2];
+    Slot out[NOUT];
+    int next_out = 0;
     int device = 0;
-    // ---- pool for parallel memcpy (pageable -> pinned)
     int nthreads = 1;
     std::vector<std::thread> pool;
+    struct Task {
+        int kind;                 // 0: stage `len` bytes from src into a slot and copy them to d_dst on `stream`; 1: drain out[slot] into dst
+        const char *src; char *d_dst; cudaStream_t stream;
+        int slot; char *dst;
+        size_t len;
+    };
+    std::deque<Task> q_in, q_out;   // separate queues and threads per direction: a drain task blocks on a GPU event that may
+    int n_in = 1;                   // be a whole chunk of compute away, and must never sit in front of the next chunk's uploads
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
-    char *j_dst = nullptr;
-    const char *j_src = nullptr;
-    size_t j_len = 0;
-    uint64_t gen = 0;
-    int remaining = 0;
-    bool stop = false;
-    // ---- drain thread (pinned -> pageable)
-    struct Item { int slot; char *dst; size_t len; };
-    std::thread drain;
-    std::deque<Item> q;
-    std::mutex qmu;
-    std::condition_variable qcv, qfree;
+    size_t h2d_pending = 0;       // staged H2D tasks queued or running (the queueing thread waits for 0: all copies ISSUED)
+    size_t d2h_inflight = 0;
     int out_busy[NOUT] = {};
-    size_t inflight = 0;
-    uint64_t staged_in = 0, staged_out = 0;     // bytes that went through the rings (p2b_io_stats)
+    bool stop = false;
     bool ok = true;
+    uint64_t staged_in = 0, staged_out = 0;     // bytes that went through the rings (p2b_io_stats)
 };
 
-static void piece(const HostIO *io, int t, size_t &lo, size_t &hi) {
-    const size_t per = ((io->j_len + io->nthreads - 1) / io->nthreads + 4095) & ~(size_t)4095;
-    lo = std::min(io->j_len, per * (size_t)t);
-    hi = std::min(io->j_len, lo + per);
-}
-static void pool_main(HostIO *io, int t) {
-    uint64_t seen = 0;
-    for (;;) {
-        std::unique_lock<std::mutex> lk(io->mu);
-        io->cv_work.wait(lk, [&] { return io->stop || io->gen != seen; });
-        if (io->stop) return;
-        seen = io->gen;
-        size_t lo, hi;
-        piece(io, t, lo, hi);
-        char *d = io->j_dst;
-        const char *s = io->j_src;
-        lk.unlock();
-        if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
-        lk.lock();
-        if (--io->remaining == 0) io->cv_done.notify_one();
-    }
-}
-static void par_memcpy(HostIO *io, char *dst, const char *src, size_t len) {
-    if (io->nthreads <= 1 || len < ((size_t)1 << 20)) { memcpy(dst, src, len); return; }
-    {
-        std::lock_guard<std::mutex> lk(io->mu);
-        io->j_dst = dst; io->j_src = src; io->j_len = len;
-        io->remaining = io->nthreads - 1;
-        io->gen++;
-    }
-    io->cv_work.notify_all();
-    size_t lo, hi;
-    piece(io, 0, lo, hi);
-    if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
-    std::unique_lock<std::mutex> lk(io->mu);
-    io->cv_done.wait(lk, [&] { return io->remaining == 0; });
-}
-static void drain_main(HostIO *io) {
+static void worker_main(HostIO *io, int t) {
     cudaSetDevice(io->device);
+    int flip = 0;
+    std::deque<HostIO::Task> &q = t < io->n_in ? io->q_in : io->q_out;
     for (;;) {
-        HostIO::Item it;
+        HostIO::Task k;
         {
-            std::unique_lock<std::mutex> lk(io->qmu);
-            io->qcv.wait(lk, [&] { return io->stop || !io->q.empty(); });
-            if (io->q.empty()) return;          // stop requested and nothing left
-            it = io->q.front();
-            io->q.pop_front();
+            std::unique_lock<std::mutex> lk(io->mu);
+            io->cv_work.wait(lk, [&] { return io->stop || !q.empty(); });
+            if (q.empty()) return;              // stop requested and nothing left
+            k = q.front();
+            q.pop_front();
         }
-        if (cudaEventSynchronize(io->out[it.slot].ev) != cudaSuccess) io->ok = false;
-        else memcpy(it.dst, io->out[it.slot].buf, it.len);
+        bool good = true;
+        if (k.kind == 0) {
+            HostIO::Slot &sl = io->in[t][flip];
+            flip ^= 1;
+            good = cudaEventSynchronize(sl.ev) == cudaSuccess;          // this worker's previous copy out of the slot has finished
+            if (good) {
+                memcpy(sl.buf, k.src, k.len);
+                good = cudaMemcpyAsync(k.d_dst, sl.buf, k.len, cudaMemcpyHostToDevice, k.stream) == cudaSuccess &&
+                       cudaEventRecord(sl.ev, k.stream) == cudaSuccess;
+            }
+        } else {
+            good = cudaEventSynchronize(io->out[k.slot].ev) == cudaSuccess;
+            if (good) memcpy(k.dst, io->out[k.slot].buf, k.len);
+        }
         {
-            std::lock_guard<std::mutex> lk(io->qmu);
-            io->out_busy[it.slot] = 0;
-            io->inflight--;
+            std::lock_guard<std::mutex> lk(io->mu);
+            if (!good) io->ok = false;
+            if (k.kind == 0) io->h2d_pending--;
+            else { io->out_busy[k.slot] = 0; io->d2h_inflight--; }
         }
-        io->qfree.notify_all();
+        io->cv_done.notify_all();
     }
 }
 
@@ -116,20 +96,24 @@ static HostIO *io_get(Ctx *c) {
     if (c->io) return c->io;
     HostIO *io = new HostIO();
     io->device = c->device;
-    bool ok = true;
-    for (auto &s : io->in) ok = ok && cudaHostAlloc((void **)&s.buf, HostIO::SLOT, cudaHostAllocDefault) == cudaSuccess &&
-                                cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
-    for (auto &s : io->out) ok = ok && cudaHostAlloc((void **)&s.buf, HostIO::SLOT, cudaHostAllocDefault) == cudaSuccess &&
-                                 cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) { delete io; return nullptr; }        // (slots leak on this path; the ctx is unusable anyway)
     int nt = 6;
     if (const char *e = getenv("P2B_COPY_THREADS")) nt = atoi(e);
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && nt > hw) nt = hw;
     if (nt < 1) nt = 1;
+    if (nt > HostIO::MAXT) nt = HostIO::MAXT;
     io->nthreads = nt;
-    for (int t = 1; t < nt; t++) io->pool.emplace_back(pool_main, io, t);
-    io->drain = std::thread(drain_main, io);
+    io->n_in = nt > 2 ? nt - (nt >= 6 ? 2 : 1) : 1;      // 6 threads: 4 upload + 2 drain
+    if (nt == 1) { nt = 2; io->nthreads = 2; }           // always at least one thread per direction
+    bool ok = true;
+    auto mk = [&](HostIO::Slot &s) {
+        ok = ok && cudaHostAlloc((void **)&s.buf, HostIO::SLOT, cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
+    };
+    for (int t = 0; t < nt; t++) { mk(io->in[t][0]); mk(io->in[t][1]); }
+    for (auto &s : io->out) mk(s);
+    if (!ok) { delete io; return nullptr; }        // (slots leak on this path; the ctx is unusable anyway)
+    for (int t = 0; t < nt; t++) io->pool.emplace_back(worker_main, io, t);
     c->io = io;
     return io;
 }
@@ -137,12 +121,10 @@ void io_destroy(Ctx *c) {
     HostIO *io = c->io;
     if (!io) return;
     { std::lock_guard<std::mutex> lk(io->mu); io->stop = true; }
-    { std::lock_guard<std::mutex> lk(io->qmu); io->stop = true; }
     io->cv_work.notify_all();
-    io->qcv.notify_all();
     for (auto &t : io->pool) t.join();
-    if (io->drain.joinable()) io->drain.join();
-    for (auto &s : io->in) { if (s.buf) cudaFreeHost(s.buf); if (s.ev) cudaEventDestroy(s.ev); }
+    for (int t = 0; t < HostIO::MAXT; t++)
+        for (auto &s : io->in[t]) { if (s.buf) cudaFreeHost(s.buf); if (s.ev) cudaEventDestroy(s.ev); }
     for (auto &s : io->out) { if (s.buf) cudaFreeHost(s.buf); if (s.ev) cudaEventDestroy(s.ev); }
     delete io;
     c->io = nullptr;
@@ -168,16 +150,20 @@ int io_h2d(Ctx *c, void *d_dst, const void *h_src, size_t bytes, cudaStream_t s)
     }
     HostIO *io = io_get(c);
     if (!io) return ctx_fail(c, P2B_ECUDA, "pinned staging buffers could not be allocated");
-    for (size_t off = 0; off < bytes; off += HostIO::SLOT) {
-        const size_t len = std::min(HostIO::SLOT, bytes - off);
-        HostIO::Slot &sl = io->in[io->next_in];
-        io->next_in = (io->next_in + 1) % HostIO::NIN;
-        P2B_CUDA(c, cudaEventSynchronize(sl.ev));              // the copy that last read this slot has finished
-        par_memcpy(io, sl.buf, (const char *)h_src + off, len);
-        P2B_CUDA(c, cudaMemcpyAsync((char *)d_dst + off, sl.buf, len, cudaMemcpyHostToDevice, s));
-        P2B_CUDA(c, cudaEventRecord(sl.ev, s));
+    {
+        std::lock_guard<std::mutex> lk(io->mu);
+        for (size_t off = 0; off < bytes; off += HostIO::SLOT) {
+            const size_t len = std::min(HostIO::SLOT, bytes - off);
+            io->q_in.push_back(HostIO::Task{0, (const char *)h_src + off, (char *)d_dst + off, s, 0, nullptr, len});
+            io->h2d_pending++;
+        }
     }
+    io->cv_work.notify_all();
+    // every slot copy has been ISSUED on `s` when this returns, so whatever the caller queues on `s` next is ordered after them
+    std::unique_lock<std::mutex> lk(io->mu);
+    io->cv_done.wait(lk, [&] { return io->h2d_pending == 0; });
     io->staged_in += bytes;
+    if (!io->ok) { io->ok = true; return ctx_fail(c, P2B_ECUDA, "a staged host-to-device copy failed"); }
     return P2B_OK;
 }
 
@@ -194,24 +180,24 @@ int io_d2h(Ctx *c, void *h_dst, const void *d_src, size_t bytes, cudaStream_t s)
         const int slot = io->next_out;
         io->next_out = (io->next_out + 1) % HostIO::NOUT;
         {
-            std::unique_lock<std::mutex> lk(io->qmu);
-            io->qfree.wait(lk, [&] { return !io->out_busy[slot]; });
+            std::unique_lock<std::mutex> lk(io->mu);
+            io->cv_done.wait(lk, [&] { return !io->out_busy[slot]; });
             io->out_busy[slot] = 1;
-            io->inflight++;
+            io->d2h_inflight++;
         }
         cudaError_t e = cudaMemcpyAsync(io->out[slot].buf, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaEventRecord(io->out[slot].ev, s);
         if (e != cudaSuccess) {
-            std::lock_guard<std::mutex> lk(io->qmu);
+            std::lock_guard<std::mutex> lk(io->mu);
             io->out_busy[slot] = 0;
-            io->inflight--;
+            io->d2h_inflight--;
             return ctx_cuda(c, e, "staged D2H");
         }
         {
-            std::lock_guard<std::mutex> lk(io->qmu);
-            io->q.push_back(HostIO::Item{slot, (char *)h_dst + off, len});
+            std::lock_guard<std::mutex> lk(io->mu);
+            io->q_out.push_back(HostIO::Task{1, nullptr, nullptr, nullptr, slot, (char *)h_dst + off, len});
         }
-        io->qcv.notify_one();
+        io->cv_work.notify_all();
     }
     io->staged_out += bytes;
     return P2B_OK;
@@ -221,8 +207,8 @@ int io_d2h(Ctx *c, void *h_dst, const void *d_src, size_t bytes, cudaStream_t s)
 int io_flush(Ctx *c) {
     HostIO *io = c->io;
     if (!io) return P2B_OK;
-    std::unique_lock<std::mutex> lk(io->qmu);
-    io->qfree.wait(lk, [&] { return io->inflight == 0; });
+    std::unique_lock<std::mutex> lk(io->mu);
+    io->cv_done.wait(lk, [&] { return io->d2h_inflight == 0; });
     if (!io->ok) { io->ok = true; return ctx_fail(c, P2B_ECUDA, "a staged device-to-host copy failed"); }
     return P2B_OK;
 }

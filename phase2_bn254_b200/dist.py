@@ -148,5 +148,13 @@ def sharded_transform(ctx, input_map, output_map, parameters, key, rank, world, 
                                  shard_count=world)
 
 
-__all__ = ["shard_range", "bind_to_gpu_numa", "all_gather_bytes", "sharded_msm", "sharded_merge_pairs",
+def sharded_contribute(ctx, params_map, out_map, delta, s_g1, r_g2, rank, world):
+    """MPCParameters::contribute with H and L split across `world` ranks (no collective: rank r rewrites only its ranges of
+    out_map, shared storage such as the mapped output file; rank 0 also writes the header, the unchanged vectors and the new
+    public key).  Every rank returns the same 64-byte contribution hash."""
+    d = np.frombuffer(int(delta).to_bytes(32, "big"), dtype=np.uint8) if isinstance(delta, int) else delta
+    return ctx.phase2_contribute(params_map, d, s_g1, r_g2, out=out_map, shard_index=rank, shard_count=world)[1]
+
+
+__all__ = ["shard_range", "sharded_contribute", "bind_to_gpu_numa", "all_gather_bytes", "sharded_msm", "sharded_merge_pairs",
            "sharded_verify_contribution", "sharded_transform", "_lib"]

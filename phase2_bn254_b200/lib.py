@@ -31,7 +31,7 @@ SYMBOLS = [
     "p2b_g1_sparse_mul", "p2b_g2_sparse_mul",
     "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
     "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants", "p2b_io_stats",
-    "p2b_g1_msm_pair", "p2b_g2_msm_pair", "p2b_g1_power_pairs", "p2b_g2_power_pairs", "p2b_random_scalars",
+    "p2b_g1_msm_pair", "p2b_g2_msm_pair", "p2b_g1_power_pairs", "p2b_g2_power_pairs", "p2b_random_scalars", "p2b_phase2_contribute_sharded",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -88,6 +88,7 @@ def load():
     lib.p2b_pot_transform.argtypes = [vp, u8p, u64, u8p, u64, u32, u32, i32, i32, i32, u8p, u8p, u8p, u32, u32]
     lib.p2b_phase2_transcript.argtypes = [vp, u8p, u64, u8p, u8p, u8p]
     lib.p2b_phase2_contribute.argtypes = [vp, u8p, u64, u8p, u64, u8p, u8p, u8p, u8p]
+    lib.p2b_phase2_contribute_sharded.argtypes = [vp, u8p, u64, u8p, u64, u8p, u8p, u8p, u8p, u32, u32]
     if hasattr(lib, "p2b_fr_fft"):
         lib.p2b_fr_fft.argtypes = [vp, u8p, u32, i32, i32]
         lib.p2b_fr_fft_dev.argtypes = [vp, vp, u32, i32, i32]
@@ -362,13 +363,13 @@ class Context:
                                                    _ptr(out)))
         return out.tobytes()
 
-    def phase2_contribute(self, params, delta, s_g1, r_g2, out=None):
+    def phase2_contribute(self, params, delta, s_g1, r_g2, out=None, shard_index=0, shard_count=1):
         p = _host(params)
         if out is None:
             out = np.empty(p.size + 384, dtype=np.uint8)
         h = np.empty(64, dtype=np.uint8)
-        self._check(self.lib.p2b_phase2_contribute(self.h, _ptr(p), p.size, _ptr(out), out.size, _ptr(_host(delta)),
-                                                   _ptr(_host(s_g1)), _ptr(_host(r_g2)), _ptr(h)))
+        self._check(self.lib.p2b_phase2_contribute_sharded(self.h, _ptr(p), p.size, _ptr(out), out.size, _ptr(_host(delta)),
+                                                           _ptr(_host(s_g1)), _ptr(_host(r_g2)), _ptr(h), shard_index, shard_count))
         return out[: p.size + 384], h.tobytes()
 
     # -- MSM

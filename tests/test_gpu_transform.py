@@ -236,3 +236,19 @@ def test_mpc_parameters_read_checked(ctx):
     bad[lay["a"][0]: lay["a"][0] + 32] = (2**256 - 1).to_bytes(32, "big")      # flag bits + coordinate >= q
     with pytest.raises(IOError):
         MPCParameters.read(bytes(bad), False, False, ctx=ctx)
+
+
+def test_phase2_contribute_sharded_equals_whole(ctx, oracle):
+    """H and L split into contiguous ranges (one per GPU): the shards, run one after the other into the same output buffer,
+    produce the bytes of the unsharded call, and every shard returns the same contribution hash."""
+    buf = synthetic_params(oracle, 301, 1)
+    delta = be(0x0fedcba987654321fedcba987654321fedcba987654321fedcba987654321 % R_MOD)
+    s = random_points(oracle, 0, 1, 77)
+    r = random_points(oracle, 1, 1, 78)
+    exp_file, exp_hash = oracle.phase2_contribute(buf, delta, s, r, threads=8)
+    b = np.frombuffer(buf, dtype=np.uint8)
+    for shards in (2, 3, 8):
+        out = np.zeros(b.size + 384, dtype=np.uint8)
+        hashes = {ctx.phase2_contribute(b, delta, s, r, out=out, shard_index=i, shard_count=shards)[1] for i in reversed(range(shards))}
+        assert hashes == {exp_hash}
+        assert out.tobytes() == exp_file
