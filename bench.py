@@ -619,12 +619,21 @@ def run_ours(args, rank, world, local_rank):
     acc_ms, acc_k = prof["accumulate"]
     acc_avg_ms = acc_ms / max(1, args.steps)       # the accumulation of one MSM (one launch per window group)
     achieved = 96.0 * n / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms else None
-    traffic = pipe_busy = mul_peak = None
+    traffic = pipe_busy = mul_peak = capture = None
     try:
         prof_json = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof_json.get("k_msm_accumulate<Fq>@2^%d" % args.log_n)
-        pipe_busy = prof_json.get("k_msm_accumulate<Fq>@2^%d:fmaheavy_busy" % args.log_n)
         mul_peak = prof_json.get("mont_mul_peak_gmul_per_s")
+        key = "k_msm_accumulate<Fq>@2^%d" % args.log_n
+        capture = prof_json.get(key + ":capture")
+        # the ncu figures are only printed when they were captured from the kernel sources this run was built from
+        import hashlib
+        h = hashlib.sha256()
+        for f in (capture or {}).get("sources", []):
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        if capture and h.hexdigest()[:16] == capture.get("source_sha256_16"):
+            traffic, pipe_busy = prof_json.get(key), prof_json.get(key + ":fmaheavy_busy")
+        elif capture:
+            capture = dict(capture, stale="kernel sources changed since the capture: traffic / busy_frac withheld")
     except (OSError, ValueError):
         pass
     line = {
@@ -644,6 +653,7 @@ def run_ours(args, rank, world, local_rank):
                      "kernel_ms": round(acc_avg_ms, 4), "launches_per_step": int(acc_k // max(1, args.steps)),
                      "limiting_pipe": {"pipe": "fma-heavy (IMAD.WIDE)", "busy_frac": pipe_busy,
                                        "source": "ncu capture committed under profiles/ (not measured live)"},
+                     "ncu_capture": capture,
                      "note": "bound by the integer multiplier pipe, not by HBM (see DESIGN.md section 4); traffic = DRAM bytes "
                              "of the accumulation of one MSM from the ncu capture; kernel time / step time = %.2f (the "
                              "sort of the next window group runs concurrently)" % (acc_avg_ms / dev_ms if dev_ms else 0)},

@@ -208,6 +208,22 @@ def field_op(field, op, a, b=bytes(32)):
     return bytes(out) if ok else None
 
 
+def fq2_pow_raw(c0, c1, e):
+    """(c0 + c1 u)^e for integers c0, c1, e: the result's raw Montgomery limbs ([c0 limbs], [c1 limbs]) as lists of 4 u64."""
+    out = (ctypes.c_uint64 * 8)()
+    ok = lib().orc_fq2_pow_raw(_cbuf(int(c0).to_bytes(32, "big")), _cbuf(int(c1).to_bytes(32, "big")),
+                               _cbuf(int(e).to_bytes(32, "big")), out)
+    assert ok
+    return list(out[:4]), list(out[4:])
+
+
+def fq2_mul_raw(a, b):
+    """Product of two Fq2 elements given (and returned) as raw Montgomery limbs ([c0 limbs], [c1 limbs])."""
+    out = (ctypes.c_uint64 * 8)()
+    lib().orc_fq2_mul_raw((ctypes.c_uint64 * 8)(*(a[0] + a[1])), (ctypes.c_uint64 * 8)(*(b[0] + b[1])), out)
+    return list(out[:4]), list(out[4:])
+
+
 def constants():
     out = (ctypes.c_uint64 * 16)()
     lib().orc_constants(out)

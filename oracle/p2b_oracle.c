@@ -729,6 +729,25 @@ int orc_field_op(int field, int op, const uint8_t *a_be, const uint8_t *b_be, ui
     uint64_t r[4]; f_into_repr(r, &a, p); r_to_be(r, out_be);
     return 1;
 }
+/* Fq2 KAT access: out = (c0 + c1 u)^e and the product a * b, operands as 32-byte BE canonical coordinates, results as RAW
+ * MONTGOMERY LIMBS (8 x u64: c0 then c1) so that they compare directly with the reference's hard-coded tables
+ * (pairing/src/bn256/fq.rs:87-432: XI_TO_Q_MINUS_1_OVER_2, FROBENIUS_COEFF_FQ6_C1 / C2, FROBENIUS_COEFF_FQ12_C1 are powers
+ * of 9 + u computed with the Fq2 arithmetic under test). */
+int orc_fq2_pow_raw(const uint8_t *c0_be, const uint8_t *c1_be, const uint8_t *e_be, uint64_t *out_limbs) {
+    fq2 a;
+    if (!fq_read(&a.c0, c0_be) || !fq_read(&a.c1, c1_be)) return 0;
+    uint64_t e[4]; r_from_be(e, e_be);
+    fq2 r = fq2_pow(&a, e, 4);
+    memcpy(out_limbs, r.c0.l, 32); memcpy(out_limbs + 4, r.c1.l, 32);
+    return 1;
+}
+int orc_fq2_mul_raw(const uint64_t *a_limbs, const uint64_t *b_limbs, uint64_t *out_limbs) {
+    fq2 a, b;
+    memcpy(a.c0.l, a_limbs, 32); memcpy(a.c1.l, a_limbs + 4, 32); memcpy(b.c0.l, b_limbs, 32); memcpy(b.c1.l, b_limbs + 4, 32);
+    fq2_mul(&a, &b);
+    memcpy(out_limbs, a.c0.l, 32); memcpy(out_limbs + 4, a.c1.l, 32);
+    return 1;
+}
 /* raw Montgomery limbs of constants, for pinning against the reference's hard-coded tables */
 void orc_constants(uint64_t *out /* 4 x {R mod q, R^2 mod q, R mod r, R^2 mod r} */) {
     memcpy(out, FQ.one, 32); memcpy(out + 4, FQ.r2, 32); memcpy(out + 8, FR.one, 32); memcpy(out + 12, FR.r2, 32);

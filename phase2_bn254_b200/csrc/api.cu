@@ -480,7 +480,7 @@ extern "C" {
 
 const char *p2b_version(void) { return "p2b 0.1 (sm_100a)"; }
 
-int p2b_init(int device, p2b_ctx **out) {
+int p2b_init(int device, p2b_ctx **out) { P2B_RANGE("p2b_init");
     if (!out) return P2B_EARG;
     *out = nullptr;
     int count = 0;
@@ -506,7 +506,7 @@ int p2b_init(int device, p2b_ctx **out) {
     return P2B_OK;
 }
 
-void p2b_destroy(p2b_ctx *h) {
+void p2b_destroy(p2b_ctx *h) { P2B_RANGE("p2b_destroy");
     if (!h) return;
     Ctx *c = &h->c;
     cudaSetDevice(c->device);
@@ -564,35 +564,35 @@ int p2b_profile_read(p2b_ctx *h, int slot, double *total_ms, uint64_t *kernels) 
     return P2B_OK;
 }
 
-int p2b_g1_batch_mul(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) {
+int p2b_g1_batch_mul(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) { P2B_RANGE("p2b_g1_batch_mul");
     return h ? host_batch(&h->c, 0, in, out, n, s, ns, ie, oe, fl) : P2B_EARG;
 }
-int p2b_g2_batch_mul(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) {
+int p2b_g2_batch_mul(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) { P2B_RANGE("p2b_g2_batch_mul");
     return h ? host_batch(&h->c, 1, in, out, n, s, ns, ie, oe, fl) : P2B_EARG;
 }
 int p2b_g1_batch_mul_powers(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t tau[32], const uint8_t *coeff,
-                            uint64_t start, int ie, int oe, int fl) {
+                            uint64_t start, int ie, int oe, int fl) { P2B_RANGE("p2b_g1_batch_mul_powers");
     return h ? host_batch_powers(&h->c, 0, in, out, n, tau, coeff, start, ie, oe, fl) : P2B_EARG;
 }
 int p2b_g2_batch_mul_powers(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, const uint8_t tau[32], const uint8_t *coeff,
-                            uint64_t start, int ie, int oe, int fl) {
+                            uint64_t start, int ie, int oe, int fl) { P2B_RANGE("p2b_g2_batch_mul_powers");
     return h ? host_batch_powers(&h->c, 1, in, out, n, tau, coeff, start, ie, oe, fl) : P2B_EARG;
 }
-int p2b_g1_batch_mul_dev(p2b_ctx *h, const void *in, void *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) {
+int p2b_g1_batch_mul_dev(p2b_ctx *h, const void *in, void *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) { P2B_RANGE("p2b_g1_batch_mul_dev");
     return h ? dev_batch(&h->c, 0, in, out, n, s, ns, ie, oe, fl) : P2B_EARG;
 }
-int p2b_g2_batch_mul_dev(p2b_ctx *h, const void *in, void *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) {
+int p2b_g2_batch_mul_dev(p2b_ctx *h, const void *in, void *out, size_t n, const uint8_t *s, size_t ns, int ie, int oe, int fl) { P2B_RANGE("p2b_g2_batch_mul_dev");
     return h ? dev_batch(&h->c, 1, in, out, n, s, ns, ie, oe, fl) : P2B_EARG;
 }
 int p2b_g1_batch_mul_powers_dev(p2b_ctx *h, const void *in, void *out, size_t n, const uint8_t tau[32], const uint8_t *coeff,
-                                uint64_t start, int ie, int oe, int fl) {
+                                uint64_t start, int ie, int oe, int fl) { P2B_RANGE("p2b_g1_batch_mul_powers_dev");
     return h ? dev_batch_powers(&h->c, 0, in, out, n, tau, coeff, start, ie, oe, fl) : P2B_EARG;
 }
 int p2b_g2_batch_mul_powers_dev(p2b_ctx *h, const void *in, void *out, size_t n, const uint8_t tau[32], const uint8_t *coeff,
-                                uint64_t start, int ie, int oe, int fl) {
+                                uint64_t start, int ie, int oe, int fl) { P2B_RANGE("p2b_g2_batch_mul_powers_dev");
     return h ? dev_batch_powers(&h->c, 1, in, out, n, tau, coeff, start, ie, oe, fl) : P2B_EARG;
 }
-int p2b_sync(p2b_ctx *h) {
+int p2b_sync(p2b_ctx *h) { P2B_RANGE("p2b_sync");
     if (!h) return P2B_EARG;
     int rc = ctx_collect_error(&h->c);
     cudaMemsetAsync(h->c.d_err, 0xff, sizeof(unsigned long long), h->c.stream);
@@ -604,37 +604,37 @@ uint64_t p2b_pot_accumulator_size(uint32_t size_log2, int compressed) { return a
 int p2b_pot_transform(p2b_ctx *h, const uint8_t *challenge, uint64_t challenge_len, uint8_t *response, uint64_t response_len,
                       uint32_t size_log2, uint32_t batch_size, int in_compressed, int out_compressed, int check_input,
                       const uint8_t tau[32], const uint8_t alpha[32], const uint8_t beta[32], uint32_t shard_index,
-                      uint32_t shard_count) {
+                      uint32_t shard_count) { P2B_RANGE("p2b_pot_transform");
     return h ? pot_transform(&h->c, challenge, challenge_len, response, response_len, size_log2, batch_size, in_compressed,
                              out_compressed, check_input, tau, alpha, beta, shard_index, shard_count)
              : P2B_EARG;
 }
 
 int p2b_pot_decompress(p2b_ctx *h, const uint8_t *response, uint64_t response_len, uint8_t *challenge, uint64_t challenge_len,
-                       uint32_t size_log2, int check_input, uint32_t shard_index, uint32_t shard_count) {
+                       uint32_t size_log2, int check_input, uint32_t shard_index, uint32_t shard_count) { P2B_RANGE("p2b_pot_decompress");
     return h ? pot_transform(&h->c, response, response_len, challenge, challenge_len, size_log2, 1, 1, 0, check_input, nullptr,
                              nullptr, nullptr, shard_index, shard_count, true)
              : P2B_EARG;
 }
-int p2b_g1_recode(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, int ie, int oe, int fl) {
+int p2b_g1_recode(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, int ie, int oe, int fl) { P2B_RANGE("p2b_g1_recode");
     return h ? host_recode(&h->c, 0, in, out, n, ie, oe, fl) : P2B_EARG;
 }
-int p2b_g2_recode(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, int ie, int oe, int fl) {
+int p2b_g2_recode(p2b_ctx *h, const uint8_t *in, uint8_t *out, size_t n, int ie, int oe, int fl) { P2B_RANGE("p2b_g2_recode");
     return h ? host_recode(&h->c, 1, in, out, n, ie, oe, fl) : P2B_EARG;
 }
 
 int p2b_phase2_transcript(p2b_ctx *h, const uint8_t *params, uint64_t params_len, const uint8_t delta[32], const uint8_t s[64],
-                          uint8_t transcript_out[64]) {
+                          uint8_t transcript_out[64]) { P2B_RANGE("p2b_phase2_transcript");
     if (!h || !params || !delta || !s || !transcript_out) return P2B_EARG;
     return phase2_transcript(&h->c, params, params_len, delta, s, nullptr, transcript_out);
 }
 int p2b_phase2_contribute(p2b_ctx *h, const uint8_t *params, uint64_t params_len, uint8_t *params_out, uint64_t params_out_len,
-                          const uint8_t delta[32], const uint8_t s[64], const uint8_t r[128], uint8_t hash_out[64]) {
+                          const uint8_t delta[32], const uint8_t s[64], const uint8_t r[128], uint8_t hash_out[64]) { P2B_RANGE("p2b_phase2_contribute");
     return h ? phase2_contribute(&h->c, params, params_len, params_out, params_out_len, delta, s, r, hash_out) : P2B_EARG;
 }
 int p2b_phase2_contribute_sharded(p2b_ctx *h, const uint8_t *params, uint64_t params_len, uint8_t *params_out, uint64_t params_out_len,
                                   const uint8_t delta[32], const uint8_t s[64], const uint8_t r[128], uint8_t hash_out[64],
-                                  uint32_t shard_index, uint32_t shard_count) {
+                                  uint32_t shard_index, uint32_t shard_count) { P2B_RANGE("p2b_phase2_contribute_sharded");
     return h ? phase2_contribute(&h->c, params, params_len, params_out, params_out_len, delta, s, r, hash_out, shard_index, shard_count)
              : P2B_EARG;
 }

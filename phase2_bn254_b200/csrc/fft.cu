@@ -439,10 +439,10 @@ static int fft_dev(Ctx *c, void *d_data, uint32_t log_n, int inverse, int coset)
 
 using namespace p2b;
 extern "C" {
-int p2b_fr_fft(p2b_ctx *h, uint8_t *data, uint32_t log_n, int inverse, int coset) {
+int p2b_fr_fft(p2b_ctx *h, uint8_t *data, uint32_t log_n, int inverse, int coset) { P2B_RANGE("p2b_fr_fft");
     return h ? fft_host(&h->c, data, log_n, inverse, coset) : P2B_EARG;
 }
-int p2b_fr_fft_dev(p2b_ctx *h, void *d_data, uint32_t log_n, int inverse, int coset) {
+int p2b_fr_fft_dev(p2b_ctx *h, void *d_data, uint32_t log_n, int inverse, int coset) { P2B_RANGE("p2b_fr_fft_dev");
     return h ? fft_dev(&h->c, d_data, log_n, inverse, coset) : P2B_EARG;
 }
 }

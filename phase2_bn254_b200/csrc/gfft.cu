@@ -299,15 +299,15 @@ static int prepare_phase2(Ctx *c, const uint8_t *acc, uint64_t acc_len, uint32_t
 
 using namespace p2b;
 extern "C" {
-int p2b_g1_group_fft(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags) {
+int p2b_g1_group_fft(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags) { P2B_RANGE("p2b_g1_group_fft");
     return h ? group_fft_host<Fq>(&h->c, 0, in, out, log_d, inverse, in_enc, out_enc, flags) : P2B_EARG;
 }
-int p2b_g2_group_fft(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags) {
+int p2b_g2_group_fft(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags) { P2B_RANGE("p2b_g2_group_fft");
     return h ? group_fft_host<Fq2>(&h->c, 1, in, out, log_d, inverse, in_enc, out_enc, flags) : P2B_EARG;
 }
 uint64_t p2b_pot_radix_file_size(uint32_t m) { return radix_file_size(m); }
 int p2b_pot_prepare_phase2(p2b_ctx *h, const uint8_t *accumulator, uint64_t accumulator_len, uint32_t size_log2, int compressed_input,
-                           int check_input, uint32_t m, uint8_t *out, uint64_t out_len, int flags) {
+                           int check_input, uint32_t m, uint8_t *out, uint64_t out_len, int flags) { P2B_RANGE("p2b_pot_prepare_phase2");
     return h ? prepare_phase2(&h->c, accumulator, accumulator_len, size_log2, compressed_input, check_input, m, out, out_len, flags)
              : P2B_EARG;
 }

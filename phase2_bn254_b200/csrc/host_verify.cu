@@ -7,6 +7,7 @@
 #include <memory>
 #include <vector>
 #include "../../include/p2b.h"
+#include "p2b_internal.h"
 #include "pairing.cuh"
 
 using namespace p2b;
@@ -65,7 +66,7 @@ template <class F> int host_mul(const uint8_t *point, const uint8_t scalar_be[32
 
 extern "C" {
 
-int p2b_pairing_check(const uint8_t *g1_points, const uint8_t *g2_points, size_t n, int *is_one) {
+int p2b_pairing_check(const uint8_t *g1_points, const uint8_t *g2_points, size_t n, int *is_one) { P2B_RANGE("p2b_pairing_check");
     if (!is_one || (n && (!g1_points || !g2_points))) return P2B_EARG;
     std::vector<Aff<Fq>> ps(n);
     std::vector<Aff<Fq2>> qs(n);
@@ -81,7 +82,7 @@ int p2b_pairing_check(const uint8_t *g1_points, const uint8_t *g2_points, size_t
     return P2B_OK;
 }
 
-int p2b_same_ratio(const uint8_t g1_a[64], const uint8_t g1_b[64], const uint8_t g2_a[128], const uint8_t g2_b[128], int *same) {
+int p2b_same_ratio(const uint8_t g1_a[64], const uint8_t g1_b[64], const uint8_t g2_a[128], const uint8_t g2_b[128], int *same) { P2B_RANGE("p2b_same_ratio");
     if (!same || !g1_a || !g1_b || !g2_a || !g2_b) return P2B_EARG;
     Aff<Fq> p[2];
     Aff<Fq2> q[2];
@@ -95,7 +96,7 @@ int p2b_same_ratio(const uint8_t g1_a[64], const uint8_t g1_b[64], const uint8_t
     return P2B_OK;
 }
 
-int p2b_hash_to_g2(const uint8_t digest[32], uint8_t out[128]) {
+int p2b_hash_to_g2(const uint8_t digest[32], uint8_t out[128]) { P2B_RANGE("p2b_hash_to_g2");
     if (!digest || !out) return P2B_EARG;
     Aff<Fq2> a;
     const bool ok = hash_to_g2(a, digest);
@@ -143,11 +144,11 @@ int p2b_rng_g2(uint8_t state[P2B_RNG_STATE_BYTES], uint8_t out[128]) {
     return P2B_OK;
 }
 
-int p2b_host_g1_mul(const uint8_t point[64], const uint8_t scalar_be32[32], uint8_t out[64]) {
+int p2b_host_g1_mul(const uint8_t point[64], const uint8_t scalar_be32[32], uint8_t out[64]) { P2B_RANGE("p2b_host_g1_mul");
     if (!point || !scalar_be32 || !out) return P2B_EARG;
     return host_mul<Fq>(point, scalar_be32, out);
 }
-int p2b_host_g2_mul(const uint8_t point[128], const uint8_t scalar_be32[32], uint8_t out[128]) {
+int p2b_host_g2_mul(const uint8_t point[128], const uint8_t scalar_be32[32], uint8_t out[128]) { P2B_RANGE("p2b_host_g2_mul");
     if (!point || !scalar_be32 || !out) return P2B_EARG;
     return host_mul<Fq2>(point, scalar_be32, out);
 }

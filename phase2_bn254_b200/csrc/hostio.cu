@@ -21,9 +21,13 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "p2b_internal.h"
 
 namespace p2b {
+
+NvtxRange::NvtxRange(const char *name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 struct HostIO {
     static constexpr size_t SLOT = (size_t)8 << 20;

@@ -198,35 +198,35 @@ static int pair_call(p2b_ctx *h, int g2, const uint8_t *pa, const uint8_t *pb, c
     return msm_call(&h->c, a);
 }
 extern "C" {
-int p2b_g1_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) { return single(h, 0, false, points, scalars, n, out); }
-int p2b_g2_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) { return single(h, 1, false, points, scalars, n, out); }
-int p2b_g1_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) { return single(h, 0, true, d_points, d_scalars, n, out); }
-int p2b_g2_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) { return single(h, 1, true, d_points, d_scalars, n, out); }
+int p2b_g1_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) { P2B_RANGE("p2b_g1_msm"); return single(h, 0, false, points, scalars, n, out); }
+int p2b_g2_msm(p2b_ctx *h, const uint8_t *points, const uint8_t *scalars, size_t n, uint8_t *out) { P2B_RANGE("p2b_g2_msm"); return single(h, 1, false, points, scalars, n, out); }
+int p2b_g1_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) { P2B_RANGE("p2b_g1_msm_dev"); return single(h, 0, true, d_points, d_scalars, n, out); }
+int p2b_g2_msm_dev(p2b_ctx *h, const void *d_points, const void *d_scalars, size_t n, uint8_t *out) { P2B_RANGE("p2b_g2_msm_dev"); return single(h, 1, true, d_points, d_scalars, n, out); }
 int p2b_g1_msm_pair(p2b_ctx *h, const uint8_t *points_a, const uint8_t *points_b, const uint8_t *scalars, size_t n, const uint8_t seed[32],
-                    uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]) {
+                    uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]) { P2B_RANGE("p2b_g1_msm_pair");
     return pair_call(h, 0, points_a, points_b, scalars, n, seed, scalar_bits, in_enc, flags, out_a, out_b, false);
 }
 int p2b_g2_msm_pair(p2b_ctx *h, const uint8_t *points_a, const uint8_t *points_b, const uint8_t *scalars, size_t n, const uint8_t seed[32],
-                    uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]) {
+                    uint32_t scalar_bits, int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]) { P2B_RANGE("p2b_g2_msm_pair");
     return pair_call(h, 1, points_a, points_b, scalars, n, seed, scalar_bits, in_enc, flags, out_a, out_b, false);
 }
 int p2b_g1_power_pairs(p2b_ctx *h, const uint8_t *points, size_t n_points, const uint8_t *scalars, const uint8_t seed[32], uint32_t scalar_bits,
-                       int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]) {
+                       int in_enc, int flags, uint8_t out_a[64], uint8_t out_b[64]) { P2B_RANGE("p2b_g1_power_pairs");
     if (h && n_points < 1) return ctx_fail(&h->c, P2B_EARG, "power_pairs needs at least one point");
     return pair_call(h, 0, points, nullptr, scalars, n_points - 1, seed, scalar_bits, in_enc, flags, out_a, out_b, true);
 }
 int p2b_g2_power_pairs(p2b_ctx *h, const uint8_t *points, size_t n_points, const uint8_t *scalars, const uint8_t seed[32], uint32_t scalar_bits,
-                       int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]) {
+                       int in_enc, int flags, uint8_t out_a[128], uint8_t out_b[128]) { P2B_RANGE("p2b_g2_power_pairs");
     if (h && n_points < 1) return ctx_fail(&h->c, P2B_EARG, "power_pairs needs at least one point");
     return pair_call(h, 1, points, nullptr, scalars, n_points - 1, seed, scalar_bits, in_enc, flags, out_a, out_b, true);
 }
-int p2b_random_scalars(p2b_ctx *h, const uint8_t seed[32], uint64_t first_index, size_t n, uint32_t scalar_bits, uint8_t *out) {
+int p2b_random_scalars(p2b_ctx *h, const uint8_t seed[32], uint64_t first_index, size_t n, uint32_t scalar_bits, uint8_t *out) { P2B_RANGE("p2b_random_scalars");
     return h ? random_scalars_host(&h->c, seed, first_index, n, scalar_bits, out) : P2B_EARG;
 }
-int p2b_g1_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[64]) {
+int p2b_g1_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[64]) { P2B_RANGE("p2b_g1_sum_points");
     return h ? sum_points(&h->c, 0, points, count, out) : P2B_EARG;
 }
-int p2b_g2_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[128]) {
+int p2b_g2_sum_points(p2b_ctx *h, const uint8_t *points, size_t count, uint8_t out[128]) { P2B_RANGE("p2b_g2_sum_points");
     return h ? sum_points(&h->c, 1, points, count, out) : P2B_EARG;
 }
 }

@@ -66,6 +66,14 @@ int io_flush(Ctx *c);        // all staged D2H bytes have reached the caller's b
 void io_destroy(Ctx *c);
 void io_stats(Ctx *c, uint64_t *staged_in, uint64_t *staged_out);
 
+// NVTX range around every ABI call (header-only nvtx3: a no-op unless a profiler injects itself) -- the counterpart of the
+// reference's only tracing, the per-step log lines of bellman/src/log.rs:56-68 and the bins' progress prints
+struct NvtxRange {
+    explicit NvtxRange(const char *name);
+    ~NvtxRange();
+};
+#define P2B_RANGE(name) ::p2b::NvtxRange nvtx_range__(name)
+
 #define P2B_CUDA(c, call)                                     \
     do {                                                      \
         cudaError_t e__ = (call);                             \

@@ -234,11 +234,11 @@ template <class F> static int sparse_mul_host(Ctx *c, int g2, const uint8_t *bas
 using namespace p2b;
 extern "C" {
 int p2b_g1_sparse_mul(p2b_ctx *h, const uint8_t *bases, size_t n_bases, const uint64_t *row_offsets, const uint32_t *cols,
-                      const uint8_t *coeffs_be32, size_t n_rows, uint8_t *out) {
+                      const uint8_t *coeffs_be32, size_t n_rows, uint8_t *out) { P2B_RANGE("p2b_g1_sparse_mul");
     return h ? sparse_mul_host<Fq>(&h->c, 0, bases, n_bases, row_offsets, cols, coeffs_be32, n_rows, out) : P2B_EARG;
 }
 int p2b_g2_sparse_mul(p2b_ctx *h, const uint8_t *bases, size_t n_bases, const uint64_t *row_offsets, const uint32_t *cols,
-                      const uint8_t *coeffs_be32, size_t n_rows, uint8_t *out) {
+                      const uint8_t *coeffs_be32, size_t n_rows, uint8_t *out) { P2B_RANGE("p2b_g2_sparse_mul");
     return h ? sparse_mul_host<Fq2>(&h->c, 1, bases, n_bases, row_offsets, cols, coeffs_be32, n_rows, out) : P2B_EARG;
 }
 }

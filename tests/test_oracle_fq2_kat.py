@@ -1,0 +1,58 @@
+"""Known-answer tests that pin the ORACLE's Fq / Fq2 arithmetic to reference-produced values: the Frobenius tables the
+reference hard-codes (pairing/src/bn256/fq.rs:106-431) are powers of xi = 9 + u in Fq2,
+
+    XI_TO_Q_MINUS_1_OVER_2      = xi^((q - 1) / 2)
+    FROBENIUS_COEFF_FQ6_C1[i]   = xi^((q^i - 1) / 3)
+    FROBENIUS_COEFF_FQ6_C2[i]   = xi^((2 q^i - 2) / 3)
+    FROBENIUS_COEFF_FQ12_C1[i]  = xi^((q^i - 1) / 6)
+
+written as Montgomery limbs.  The exponents exceed 256 bits for i >= 2, so they are evaluated with the identity
+xi^((q^i - 1) / k) = prod_{j < i} frob^j(xi^((q - 1) / k)), where frob^j is conjugation for odd j: every step is an Fq2
+multiplication or a 254-bit power of the oracle (field.h fq2_mul / fq2_sqr / fq2_pow, the code under every G2 result the parity
+tests compare against).  28 x 2 field elements, bit for bit."""
+import json
+import os
+
+import pytest
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fq2_frobenius_kat.json")))["tables"]
+
+
+def entries(name):
+    v = [int(x, 16) for x in KAT[name]["limbs"]]
+    return [(v[8 * i: 8 * i + 4], v[8 * i + 4: 8 * i + 8]) for i in range(len(v) // 8)]
+
+
+def conj_raw(a):
+    """(c0, c1) -> (c0, -c1) on raw Montgomery limbs: negation commutes with the Montgomery map."""
+    c1 = sum(l << (64 * i) for i, l in enumerate(a[1]))
+    n = (Q - c1) % Q
+    return a[0], [(n >> (64 * i)) & 0xffffffffffffffff for i in range(4)]
+
+
+def xi_pow_chain(oracle, k, mult, count):
+    """[xi^(mult (q^i - 1) / k) for i < count] from one 254-bit power and Frobenius conjugations."""
+    base = oracle.fq2_pow_raw(9, 1, mult * (Q - 1) // k)
+    one = oracle.fq2_pow_raw(9, 1, 0)
+    out, acc, f = [one], one, base
+    for i in range(1, count):
+        acc = oracle.fq2_mul_raw(acc, f)          # acc = prod_{j < i} frob^j(base)
+        out.append(acc)
+        f = conj_raw(f)                           # frob^(j+1)(base): the q-power map on Fq2 is conjugation, applied to the
+        #                                           coefficient (base^q = conj(base)); base^(q^j) alternates base, conj(base)
+    return out
+
+
+def test_xi_to_q_minus_1_over_2(oracle):
+    assert oracle.fq2_pow_raw(9, 1, (Q - 1) // 2) == entries("XI_TO_Q_MINUS_1_OVER_2")[0]
+
+
+@pytest.mark.parametrize("name,k,mult,count", [("FROBENIUS_COEFF_FQ6_C1", 3, 1, 6), ("FROBENIUS_COEFF_FQ6_C2", 3, 2, 6),
+                                               ("FROBENIUS_COEFF_FQ12_C1", 6, 1, 12)])
+def test_frobenius_tables(oracle, name, k, mult, count):
+    ref = entries(name)
+    assert len(ref) == count
+    got = xi_pow_chain(oracle, k, mult, count)
+    for i in range(count):
+        assert got[i] == ref[i], "%s[%d] (%s)" % (name, i, KAT[name]["lines"])
