@@ -396,8 +396,37 @@ def scaling_extras(args, torch, np, dist, pdist, lib, ctx, rank, world, device, 
                 del r1
             del body
         out["sharded_transform_2^%d" % size] = row
+        # -- (3b) prepare_phase2 for m = 20 from that response (compressed): four group iFFTs of 2^20 points (3 G1 + 1 G2) sharded
+        #         over the ranks (rank-crossing butterfly stages exchanged over NCCL P2P, block-local transforms) + the H query
+        mp2 = min(args.prepare_m, size)
+        qf = os.path.join(d, "radix")
+        qbytes = 192 + 384 * (1 << mp2)
+        if rank == 0:
+            with open(qf, "wb") as fh:
+                fh.truncate(qbytes)
+        barrier()
+        rro = np.memmap(rf, dtype=np.uint8, mode="r")
+        qm = np.memmap(qf, dtype=np.uint8, mode="r+")
+        if (1 << mp2) >= 2 * world:
+            t = wall(lambda: pdist.sharded_prepare_phase2(ctx, rro, prm, mp2, qm, rank, world, True, True, device if world > 1 else None))
+            qm.flush()
+            barrier()
+            row = {"wall_s": round(t, 4), "ranks": world, "file_bytes": qbytes,
+                   "scalar_muls": 4 * (1 << (mp2 - 1)) * mp2 + 4 * (1 << mp2)}
+            if rank == 0:
+                img = np.memmap(qf, dtype=np.uint8, mode="r")
+                row["file_blake2b"] = hashlib.blake2b(img).hexdigest()[:32]
+                t0 = time.perf_counter()
+                one = ctx.pot_prepare_phase2(rro, size, mp2, compressed_input=True)
+                row["single_gpu_call_wall_s"] = round(time.perf_counter() - t0, 4)
+                row["equals_single_gpu_file"] = bool(np.array_equal(one, img))
+                del img, one
+            out["sharded_prepare_phase2_m%d" % mp2] = row
+        del rro, qm
         del cm, rm
         barrier()
+        if rank == 0:
+            os.remove(qf)
         if rank == 0:
             for f in (cf, rf, rf1):
                 os.remove(f)
@@ -915,6 +944,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--config5-log-n", type=int, default=25, help="scaling rows: log2 of the G1 / G2 MSM terms per GPU (config 5)")
     ap.add_argument("--sharded-transform-size", type=int, default=22, help="scaling rows: log2 of the powers of the sharded transform")
+    ap.add_argument("--prepare-m", type=int, default=20, help="scaling rows: m of the sharded prepare_phase2")
     ap.add_argument("--max-contribute-log", type=int, default=26, help="scaling rows: largest log2(constraints) of the sharded contribute")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -216,6 +216,23 @@ int p2b_g1_group_fft(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t log
                      int flags);
 int p2b_g2_group_fft(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc,
                      int flags);
+/* Multi-GPU group FFT (dist.sharded_group_fft): a transform of 2^total_log_d points block-distributed over R = 2^k GPUs is k
+ * rank-crossing decimation-in-frequency stages -- each rank computes half of the butterflies it shares with its partner,
+ *     out_sum[i] = a[i] + b[i],   out_diff[i] = [w^(start + i)] (a[i] - b[i])      (n = 2^log_n pairs; w = omega^(2^stage))
+ * and exchanges the halves (NCCL send / recv of 64 / 128 B points by the caller: about 1 % of a stage's compute time) -- followed
+ * by an ordinary transform of the rank's 2^(total_log_d - k) points whose inverse scaling is that of the whole domain
+ * (p2b_*_group_fft_scaled).  Rank r then holds X[R j + bitrev_k(r)].  w == NULL in p2b_*_gfft_stage skips the multiplication
+ * (plain sums / differences: the H query tau^(i+d) G - tau^i G of prepare_phase2.rs:132-148); either output may be NULL.
+ * p2b_fr_root_of_unity: omega_d (inverse: omega_d^-1), bellman/src/domain.rs:52-99. */
+int p2b_g1_group_fft_scaled(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc,
+                            int flags, uint32_t total_log_d);
+int p2b_g2_group_fft_scaled(p2b_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc,
+                            int flags, uint32_t total_log_d);
+int p2b_g1_gfft_stage(p2b_ctx *ctx, const uint8_t *a, const uint8_t *b, uint32_t log_n, const uint8_t *w_be_or_null, uint64_t start,
+                      int in_enc, int out_enc, int flags, uint8_t *out_sum, uint8_t *out_diff);
+int p2b_g2_gfft_stage(p2b_ctx *ctx, const uint8_t *a, const uint8_t *b, uint32_t log_n, const uint8_t *w_be_or_null, uint64_t start,
+                      int in_enc, int out_enc, int flags, uint8_t *out_sum, uint8_t *out_diff);
+int p2b_fr_root_of_unity(uint32_t log_d, int inverse, uint8_t out_be[32]);
 /* One iteration of powersoftau/src/bin/prepare_phase2.rs:62-241: from an accumulator (challenge layout, uncompressed, or
  * response layout, compressed; the 64-byte hash prefix included) to the image of the file phase1radix2m{m}:
  * alpha_g1 | beta_g1 | beta_g2 | coeffs_g1[d] | coeffs_g2[d] | alpha_coeffs_g1[d] | beta_coeffs_g1[d] | h[d-1], all

@@ -148,10 +148,17 @@ template <class F> struct GfftArea {
 };
 
 // In: a.X holds d = 2^log_d affine points (raw Montgomery).  Out: natural-order transform written to d_out in out_enc.
-template <class F> static int group_fft_dev(Ctx *c, GfftArea<F> &a, uint32_t log_d, int inverse, int g2, void *d_out, int out_enc, int flags) {
+// total_log_d (>= log_d): the inverse transform scales by 2^-total_log_d -- the block-local part of a transform of 2^total_log_d
+// points sharded over 2^(total_log_d - log_d) GPUs (dist.sharded_group_fft); 0 = log_d.
+template <class F> static int group_fft_dev(Ctx *c, GfftArea<F> &a, uint32_t log_d, int inverse, int g2, void *d_out, int out_enc, int flags,
+                                            uint32_t total_log_d = 0) {
     const size_t d = (size_t)1 << log_d;
     uint32_t omega[8], ninv[8];
     host_domain_constants(log_d, inverse, omega, ninv);
+    if (total_log_d > log_d) {
+        uint32_t unused[8];
+        host_domain_constants(total_log_d, inverse, unused, ninv);
+    }
     Fr w;
     memcpy(w.l, omega, 32);
     int rc;
@@ -196,9 +203,10 @@ static int to_raw(Ctx *c, int g2, const void *d_wire, void *d_raw, size_t n, int
 }
 
 template <class F> static int group_fft_host(Ctx *c, int g2, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc,
-                                             int flags) {
+                                             int flags, uint32_t total_log_d = 0) {
     if (!in || !out) return ctx_fail(c, P2B_EARG, "null buffer");
-    if (log_d > 28) return ctx_fail(c, P2B_EARG, "group fft: log_d must be <= 28 (Fr::S)");
+    if (log_d > 28 || total_log_d > 28 || (total_log_d && total_log_d < log_d))
+        return ctx_fail(c, P2B_EARG, "group fft: log_d <= total_log_d <= 28 (Fr::S)");
     if (in_enc < 0 || in_enc > 2 || out_enc < 0 || out_enc > 2) return ctx_fail(c, P2B_EARG, "bad encoding");
     P2B_CUDA(c, cudaSetDevice(c->device));
     c->last_error.clear();
@@ -212,8 +220,55 @@ template <class F> static int group_fft_host(Ctx *c, int g2, const uint8_t *in, 
     a.carve(c->gfft.p, d);
     if ((rc = io_h2d(c, c->stage_in[0].p, in, d * isz, c->stream))) return rc;
     if ((rc = to_raw(c, g2, c->stage_in[0].p, a.X, d, in_enc, flags, 0))) return rc;
-    if ((rc = group_fft_dev<F>(c, a, log_d, inverse, g2, c->stage_out[0].p, out_enc, flags))) return rc;
+    if ((rc = group_fft_dev<F>(c, a, log_d, inverse, g2, c->stage_out[0].p, out_enc, flags, total_log_d))) return rc;
     if ((rc = io_d2h(c, out, c->stage_out[0].p, d * osz, c->stream))) return rc;
+    return ctx_collect_error(c);
+}
+
+// One rank-crossing stage of a transform sharded over several GPUs: out_sum[i] = a[i] + b[i], out_diff[i] = [w^(start + i)] (a[i] - b[i])
+// for n = 2^log_n point pairs (w == NULL: plain differences, the H query of prepare_phase2.rs:132-148).  The same kernels as one
+// stage of group_fft_dev: butterfly -> batched normalisation -> batch_exp with the powers of w generated on the device.
+template <class F> static int gfft_stage_host(Ctx *c, int g2, const uint8_t *pa, const uint8_t *pb, uint32_t log_n, const uint8_t *w_be,
+                                              uint64_t start, int in_enc, int out_enc, int flags, uint8_t *out_sum, uint8_t *out_diff) {
+    constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
+    if (!pa || !pb || (!out_sum && !out_diff)) return ctx_fail(c, P2B_EARG, "null buffer");
+    if (log_n > 27) return ctx_fail(c, P2B_EARG, "gfft stage: log_n must be <= 27");
+    if (in_enc < 0 || in_enc > 2 || out_enc < 0 || out_enc > 2) return ctx_fail(c, P2B_EARG, "bad encoding");
+    P2B_CUDA(c, cudaSetDevice(c->device));
+    c->last_error.clear();
+    P2B_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream));
+    const size_t n = (size_t)1 << log_n, d = 2 * n, isz = enc_size(g2, in_enc), osz = enc_size(g2, out_enc);
+    int rc;
+    if ((rc = dev_reserve(c, c->gfft, GfftArea<F>::bytes(d)))) return rc;
+    if ((rc = dev_reserve(c, c->stage_in[0], d * isz))) return rc;
+    if ((rc = dev_reserve(c, c->stage_out[0], d * osz))) return rc;
+    GfftArea<F> a;
+    a.carve(c->gfft.p, d);
+    char *st = (char *)c->stage_in[0].p, *so = (char *)c->stage_out[0].p;
+    if ((rc = io_h2d(c, st, pa, n * isz, c->stream))) return rc;
+    if ((rc = io_h2d(c, st + n * isz, pb, n * isz, c->stream))) return rc;
+    if ((rc = to_raw(c, g2, st, a.X, d, in_enc, flags, 0))) return rc;
+    k_gbutterfly<F><<<grid_for(c, n), 128, 0, c->stream>>>(a.X, a.jx, a.jy, a.jz, log_n + 1, 0);     // pairs (i, i + n)
+    c->launches++;
+    if ((rc = normalize_to<F>(c, a.jx, a.jy, a.jz, a.prefix, a.N, d, ENC_RAW_MONT_LE))) return rc;
+    ScalarSpec sc;
+    memset(&sc, 0, sizeof sc);
+    sc.mode = 3;
+    if (out_sum) {
+        if ((rc = launch_batch_mul(c, g2, a.N, so, n, sc, ENC_RAW_MONT_LE, out_enc, 0, 0))) return rc;
+        if ((rc = io_d2h(c, out_sum, so, n * osz, c->stream))) return rc;
+    }
+    if (out_diff) {
+        if (w_be) {
+            memset(&sc, 0, sizeof sc);
+            sc.mode = 2;
+            sc.start = start;
+            if (!read_scalar_be(w_be, sc.tau)) return ctx_fail(c, P2B_EARG, "twiddle base not canonical");
+            sc.coeff[0] = 1;
+        }
+        if ((rc = launch_batch_mul(c, g2, a.N + n * WU, so + n * osz, n, sc, ENC_RAW_MONT_LE, out_enc, flags & P2B_G2_SUBGROUP, 0))) return rc;
+        if ((rc = io_d2h(c, out_diff, so + n * osz, n * osz, c->stream))) return rc;
+    }
     return ctx_collect_error(c);
 }
 
@@ -304,6 +359,33 @@ int p2b_g1_group_fft(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d
 }
 int p2b_g2_group_fft(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags) { P2B_RANGE("p2b_g2_group_fft");
     return h ? group_fft_host<Fq2>(&h->c, 1, in, out, log_d, inverse, in_enc, out_enc, flags) : P2B_EARG;
+}
+int p2b_g1_group_fft_scaled(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags,
+                            uint32_t total_log_d) { P2B_RANGE("p2b_g1_group_fft_scaled");
+    return h ? group_fft_host<Fq>(&h->c, 0, in, out, log_d, inverse, in_enc, out_enc, flags, total_log_d) : P2B_EARG;
+}
+int p2b_g2_group_fft_scaled(p2b_ctx *h, const uint8_t *in, uint8_t *out, uint32_t log_d, int inverse, int in_enc, int out_enc, int flags,
+                            uint32_t total_log_d) { P2B_RANGE("p2b_g2_group_fft_scaled");
+    return h ? group_fft_host<Fq2>(&h->c, 1, in, out, log_d, inverse, in_enc, out_enc, flags, total_log_d) : P2B_EARG;
+}
+int p2b_g1_gfft_stage(p2b_ctx *h, const uint8_t *a, const uint8_t *b, uint32_t log_n, const uint8_t *w_be, uint64_t start, int in_enc,
+                      int out_enc, int flags, uint8_t *out_sum, uint8_t *out_diff) { P2B_RANGE("p2b_g1_gfft_stage");
+    return h ? gfft_stage_host<Fq>(&h->c, 0, a, b, log_n, w_be, start, in_enc, out_enc, flags, out_sum, out_diff) : P2B_EARG;
+}
+int p2b_g2_gfft_stage(p2b_ctx *h, const uint8_t *a, const uint8_t *b, uint32_t log_n, const uint8_t *w_be, uint64_t start, int in_enc,
+                      int out_enc, int flags, uint8_t *out_sum, uint8_t *out_diff) { P2B_RANGE("p2b_g2_gfft_stage");
+    return h ? gfft_stage_host<Fq2>(&h->c, 1, a, b, log_n, w_be, start, in_enc, out_enc, flags, out_sum, out_diff) : P2B_EARG;
+}
+/* omega_d^(+-1) (32-byte big-endian canonical) of the 2^log_d domain: the twiddle base of a sharded transform's rank-crossing stages */
+int p2b_fr_root_of_unity(uint32_t log_d, int inverse, uint8_t out_be[32]) {
+    if (log_d > 28 || !out_be) return P2B_EARG;
+    uint32_t omega[8], ninv[8];
+    host_domain_constants(log_d, inverse, omega, ninv);
+    Fr w;
+    memcpy(w.l, omega, 32);
+    w = from_mont(w);
+    for (int i = 0; i < 8; i++) { uint32_t v = w.l[7 - i]; out_be[4 * i] = v >> 24; out_be[4 * i + 1] = v >> 16; out_be[4 * i + 2] = v >> 8; out_be[4 * i + 3] = v; }
+    return P2B_OK;
 }
 uint64_t p2b_pot_radix_file_size(uint32_t m) { return radix_file_size(m); }
 int p2b_pot_prepare_phase2(p2b_ctx *h, const uint8_t *accumulator, uint64_t accumulator_len, uint32_t size_log2, int compressed_input,

@@ -32,6 +32,7 @@ SYMBOLS = [
     "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
     "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants", "p2b_io_stats",
     "p2b_g1_msm_pair", "p2b_g2_msm_pair", "p2b_g1_power_pairs", "p2b_g2_power_pairs", "p2b_random_scalars", "p2b_phase2_contribute_sharded",
+    "p2b_g1_group_fft_scaled", "p2b_g2_group_fft_scaled", "p2b_g1_gfft_stage", "p2b_g2_gfft_stage", "p2b_fr_root_of_unity",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -97,6 +98,10 @@ def load():
     lib.p2b_g2_recode.argtypes = [vp, u8p, u8p, sz, i32, i32, i32]
     lib.p2b_g1_group_fft.argtypes = [vp, u8p, u8p, u32, i32, i32, i32, i32]
     lib.p2b_g2_group_fft.argtypes = [vp, u8p, u8p, u32, i32, i32, i32, i32]
+    for g in ("g1", "g2"):
+        getattr(lib, "p2b_%s_group_fft_scaled" % g).argtypes = [vp, u8p, u8p, u32, i32, i32, i32, i32, u32]
+        getattr(lib, "p2b_%s_gfft_stage" % g).argtypes = [vp, u8p, u8p, u32, u8p, u64, i32, i32, i32, u8p, u8p]
+    lib.p2b_fr_root_of_unity.argtypes = [u32, i32, u8p]
     lib.p2b_pot_radix_file_size.argtypes = [u32]
     lib.p2b_pot_radix_file_size.restype = u64
     lib.p2b_pot_prepare_phase2.argtypes = [vp, u8p, u64, u32, i32, i32, u32, u8p, u64, i32]
@@ -178,6 +183,13 @@ def hash_to_g2(digest):
     out = np.empty(128, dtype=np.uint8)
     _hostcall("p2b_hash_to_g2", _ptr(d), _ptr(out))
     return out.tobytes()
+
+
+def root_of_unity(log_d, inverse=False):
+    """omega of the 2^log_d evaluation domain (bellman/src/domain.rs:52-99) as an int; inverse: omega^-1."""
+    out = np.empty(32, dtype=np.uint8)
+    _hostcall("p2b_fr_root_of_unity", int(log_d), int(bool(inverse)), _ptr(out))
+    return int.from_bytes(out.tobytes(), "big")
 
 
 def host_mul(group, point, scalar_be32):
@@ -467,6 +479,35 @@ class Context:
         fn = self.lib.p2b_g2_group_fft if group == G2 else self.lib.p2b_g1_group_fft
         self._check(fn(self.h, _ptr(pts), _ptr(out), log_d, int(inverse), in_enc, out_enc, flags))
         return out
+
+    def group_fft_scaled(self, group, points, inverse, total_log_d, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0):
+        """group_fft whose inverse scaling is 2^-total_log_d (the block-local part of a transform sharded over several GPUs)."""
+        pts = _host(points)
+        d = pts.size // enc_size(group, in_enc)
+        log_d = d.bit_length() - 1
+        if d == 0 or (1 << log_d) != d:
+            raise P2BError(EARG, "fft length must be a power of two")
+        out = np.empty(d * enc_size(group, out_enc), dtype=np.uint8)
+        fn = self.lib.p2b_g2_group_fft_scaled if group == G2 else self.lib.p2b_g1_group_fft_scaled
+        self._check(fn(self.h, _ptr(pts), _ptr(out), log_d, int(inverse), in_enc, out_enc, flags, total_log_d))
+        return out
+
+    def gfft_stage(self, group, a, b, w=None, start=0, in_enc=ENC_UNCOMPRESSED, out_enc=ENC_UNCOMPRESSED, flags=0, want_sum=True,
+                   want_diff=True):
+        """(a + b, [w^(start+i)] (a - b)) elementwise over two arrays of 2^k points; w=None: plain differences."""
+        pa, pb = _host(a), _host(b)
+        n = pa.size // enc_size(group, in_enc)
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n or pb.size != pa.size:
+            raise P2BError(EARG, "gfft_stage: two arrays of the same power-of-two length")
+        osz = enc_size(group, out_enc)
+        s = np.empty(n * osz, dtype=np.uint8) if want_sum else None
+        d = np.empty(n * osz, dtype=np.uint8) if want_diff else None
+        wb = _fixed(w, 32, "w") if w is not None else None
+        fn = self.lib.p2b_g2_gfft_stage if group == G2 else self.lib.p2b_g1_gfft_stage
+        self._check(fn(self.h, _ptr(pa), _ptr(pb), log_n, _ptr(wb) if wb is not None else None, start, in_enc, out_enc, flags,
+                       _ptr(s) if s is not None else None, _ptr(d) if d is not None else None))
+        return s, d
 
     def pot_prepare_phase2(self, accumulator, size_log2, m, compressed_input=False, check_input=True, flags=0):
         """Image of the file phase1radix2m{m} (powersoftau/src/bin/prepare_phase2.rs:62-241)."""

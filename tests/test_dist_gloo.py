@@ -121,3 +121,48 @@ def test_shard_range_partition():
             assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _gfft_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch.distributed as dist
+    import oracle as oc
+    from phase2_bn254_b200 import dist as pdist
+    from util import random_points
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        ctx = OracleCtx(oc)
+        res = {}
+        for group, d in ((0, 16), (1, 8)):
+            size = 128 if group else 64
+            L = d // world
+            x = random_points(oc, group, d, seed=77 + group, threads=2)                   # the same vector on every rank
+            for inverse in (False, True):
+                outs, off = pdist.sharded_group_fft(ctx, group, np.frombuffer(x[rank * L * size: (rank + 1) * L * size], dtype=np.uint8),
+                                                    rank, world, inverse)
+                whole = ctx.group_fft_scaled(group, x, inverse, d.bit_length() - 1).reshape(L, world, size)   # by definition
+                res[(group, inverse)] = bool(np.array_equal(outs.reshape(L, size), whole[:, off, :]))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_group_fft_gloo(world):
+    """The multi-GPU group FFT's rank logic over real torch.distributed P2P exchanges (gloo), the oracle standing in for the
+    per-rank GPU kernels: every rank's outputs equal the transform by definition at X[world j + bitrev(rank)]."""
+    port = 30700 + os.getpid() % 500 + world
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gfft_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        assert all(res.values()), (rank, res)

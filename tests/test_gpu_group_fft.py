@@ -97,3 +97,54 @@ def test_prepare_phase2_rejects_bad_input(ctx, oracle):
     acc[64 + 64 * 2 + 63] ^= 1                                                               # tau_g1[2] off the curve
     with pytest.raises(DeserializationError):
         prepare_phase2(ctx, np.frombuffer(bytes(acc), dtype=np.uint8), params, 2, input_is_compressed=False)
+
+
+@pytest.mark.parametrize("group,log_d", [(0, 6), (1, 5)])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_group_fft_equals_single_gpu(ctx, oracle, group, log_d, world):
+    """The multi-GPU schedule (rank-crossing DIF stages through p2b_g*_gfft_stage, block-local transforms through
+    p2b_g*_group_fft_scaled, outputs at X[R j + bitrev(r)]) with all ranks simulated on one GPU: the bytes of the ordinary
+    single-GPU transform, both directions, with infinity and repeated points in the input."""
+    from phase2_bn254_b200.dist import simulate_sharded_group_fft
+    d = 1 << log_d
+    size = 128 if group else 64
+    pts = bytearray(random_points(oracle, group, d, seed=650 + log_d))
+    pts[size * 2: size * 3] = bytes([0x40]) + bytes(size - 1)
+    pts[size * 3: size * 4] = pts[0:size]
+    pts[size * (d // 2): size * (d // 2 + 1)] = pts[0:size]                # a == b across the first rank-crossing stage
+    pts = bytes(pts)
+    for inverse in (False, True):
+        exp = ctx.group_fft(group, pts, inverse).tobytes()
+        assert simulate_sharded_group_fft(ctx, group, pts, world, inverse).tobytes() == exp, (world, inverse)
+
+
+def test_gfft_stage_matches_oracle(ctx, oracle):
+    """One rank-crossing stage by itself: a + b and [w^(start+i)](a - b) against the oracle's point arithmetic."""
+    from util import OracleCtx
+    n = 16
+    for group in (0, 1):
+        a, b = random_points(oracle, group, n, seed=660 + group), random_points(oracle, group, n, seed=670 + group)
+        w = np.frombuffer(be(omega(7)), dtype=np.uint8)
+        s, dd = ctx.gfft_stage(group, a, b, w, 37)
+        es, ed = OracleCtx(oracle).gfft_stage(group, a, b, w, 37)
+        assert s.tobytes() == es.tobytes() and dd.tobytes() == ed.tobytes()
+        _, plain = ctx.gfft_stage(group, a, b, None, want_sum=False)          # w = NULL: plain differences (the H query)
+        assert plain.tobytes() == OracleCtx(oracle).gfft_stage(group, a, b, None, want_sum=False)[1].tobytes()
+
+
+@pytest.mark.parametrize("compressed", [False, True])
+def test_sharded_prepare_phase2_assembly(ctx, oracle, compressed):
+    """dist.sharded_prepare_phase2 on one rank (no exchange) writes the bytes of p2b_pot_prepare_phase2: section offsets, the
+    strided output placement and the H query's index ranges."""
+    from phase2_bn254_b200.dist import sharded_prepare_phase2
+    from phase2_bn254_b200.powersoftau import CeremonyParams
+    size = 4
+    prm = CeremonyParams(size, 8)
+    ch0 = oracle.pot_generate_initial(size)
+    acc = oracle.pot_transform(ch0, size, 8, be(TAU), be(ALPHA), be(BETA), out_compressed=compressed, threads=8)
+    amap = np.frombuffer(acc, dtype=np.uint8)
+    for m in (1, 3, 4):
+        exp = ctx.pot_prepare_phase2(amap, size, m, compressed_input=compressed)
+        out = np.zeros(exp.size, dtype=np.uint8)
+        sharded_prepare_phase2(ctx, amap, prm, m, out, 0, 1, input_is_compressed=compressed)
+        assert out.tobytes() == exp.tobytes(), m

@@ -117,3 +117,39 @@ class OracleCtx:
         n = len(v) // size
         k = self._coeffs(n - 1, scalars, seed, scalar_bits)
         return self.msm(group, v[: (n - 1) * size], k), self.msm(group, v[size:], k)
+
+    def gfft_stage(self, group, a, b, w=None, start=0, in_enc=0, out_enc=0, flags=0, want_sum=True, want_diff=True):
+        import numpy as np
+        size = 128 if group else 64
+        a, b = bytes(np.asarray(a)), bytes(np.asarray(b))
+        n = len(a) // size
+        negb = self.oc.batch_mul(group, b, be(R_MOD - 1), threads=self.threads)
+        pair = lambda x, y, i: x[i * size: (i + 1) * size] + y[i * size: (i + 1) * size]
+        sums = b"".join(self.oc.sum_points(group, pair(a, b, i)) for i in range(n)) if want_sum else None
+        diffs = None
+        if want_diff:
+            diffs = b"".join(self.oc.sum_points(group, pair(a, negb, i)) for i in range(n))
+            if w is not None:
+                wv = int.from_bytes(bytes(np.asarray(w)), "big")
+                ks = b"".join(be(pow(wv, start + i, R_MOD)) for i in range(n))
+                diffs = self.oc.batch_mul(group, diffs, ks, threads=self.threads)
+        f = lambda x: np.frombuffer(x, dtype=np.uint8) if x is not None else None
+        return f(sums), f(diffs)
+
+    def group_fft_scaled(self, group, points, inverse, total_log_d, in_enc=0, out_enc=0, flags=0):
+        """The transform by its definition X[k] = scale * sum_n w^(n k) x[n], one oracle MSM per output."""
+        import numpy as np
+        from phase2_bn254_b200 import lib
+        size = 128 if group else 64
+        pts = bytes(np.asarray(points))
+        d = len(pts) // size
+        w = lib.root_of_unity(d.bit_length() - 1, inverse)
+        scale = pow(pow(2, total_log_d, R_MOD), -1, R_MOD) if inverse else 1
+        out = b"".join(self.oc.msm(group, pts, b"".join(be(pow(w, n * k, R_MOD) * scale % R_MOD) for n in range(d)), threads=self.threads)
+                       for k in range(d))
+        return np.frombuffer(out, dtype=np.uint8)
+
+    def group_fft(self, group, points, inverse=False, in_enc=0, out_enc=0, flags=0):
+        import numpy as np
+        d = len(bytes(np.asarray(points))) // (128 if group else 64)
+        return self.group_fft_scaled(group, points, inverse, d.bit_length() - 1)
