@@ -408,6 +408,9 @@ def scaling_extras(args, torch, np, dist, pdist, lib, ctx, rank, world, device, 
         rro = np.memmap(rf, dtype=np.uint8, mode="r")
         qm = np.memmap(qf, dtype=np.uint8, mode="r+")
         if (1 << mp2) >= 2 * world:
+            # warm-up at m = 6: NCCL sets up its P2P connections on the first send / recv between a pair of ranks
+            pdist.sharded_prepare_phase2(ctx, rro, prm, 6, np.zeros(192 + 384 * 64, dtype=np.uint8), rank, world, True, True,
+                                         device if world > 1 else None)
             t = wall(lambda: pdist.sharded_prepare_phase2(ctx, rro, prm, mp2, qm, rank, world, True, True, device if world > 1 else None))
             qm.flush()
             barrier()
