@@ -29,6 +29,28 @@ P2B_HD Fq2 select(bool c, const Fq2 &b, const Fq2 &a) {
 P2B_HD Fq2 cneg(const Fq2 &a, bool c) { return select(c, neg(a), a); }
 // (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u   (fq2.rs:167-180)
 P2B_HD Fq2 mul(const Fq2 &a, const Fq2 &b) {
+#if defined(__CUDA_ARCH__) && defined(P2B_FQ2_LAZY)
+    // lazy reduction: three 512-bit products, two Montgomery reductions (336 instead of 408 wide multiply-adds)
+    //   c0 = (a0 b0 - a1 b1 + q^2) / R      in (0, 2 q^2) < q 2^256
+    //   c1 = ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) / R = (a0 b1 + a1 b0) / R   in [0, 2 q^2)
+    uint32_t t0[16], t1[16], d[16], p2[16];
+    wide_mul(t0, a.c0.l, b.c0.l);
+    wide_mul(t1, a.c1.l, b.c1.l);
+#pragma unroll
+    for (int i = 0; i < 16; i++) p2[i] = d_FQ_P2[i];
+    sub16(d, t0, t1);                    // may wrap below zero: the + q^2 brings it back (mod 2^512 arithmetic)
+    add16(d, d, p2);
+    Fq2 r;
+    mont_red<FqP>(r.c0.l, d);
+    add16(t0, t0, t1);
+    uint32_t sa[8], sb[8];
+    add8(sa, a.c0.l, a.c1.l);            // < 2q < 2^256: unreduced sums are fine as multiplier inputs
+    add8(sb, b.c0.l, b.c1.l);
+    wide_mul(t1, sa, sb);
+    sub16(t1, t1, t0);
+    mont_red<FqP>(r.c1.l, t1);
+    return r;
+#else
     Fq aa = mul(a.c0, b.c0);
     Fq bb = mul(a.c1, b.c1);
     Fq s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
@@ -36,6 +58,7 @@ P2B_HD Fq2 mul(const Fq2 &a, const Fq2 &b) {
     r.c1 = sub(sub(s, aa), bb);
     r.c0 = sub(aa, bb);
     return r;
+#endif
 }
 // (a0 + a1 u)^2 = (a0 + a1)(a0 - a1) + 2 a0 a1 u   (fq2.rs:131-145)
 P2B_HD Fq2 sqr(const Fq2 &a) {

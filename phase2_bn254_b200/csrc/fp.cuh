@@ -47,6 +47,11 @@ P2B_DEF_CONST(FR_P, {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x81815
 P2B_DEF_CONST(FR_ONE, {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u})
 P2B_DEF_CONST(FR_R2, {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u})
 
+// q^2 (16 limbs): added to a difference of two products so that it stays non-negative and below q * 2^256 (lazy reduction in Fq2)
+#if defined(__CUDACC__)
+static __device__ __constant__ uint32_t d_FQ_P2[16] = {0x275d69b1u, 0x3b5458a2u, 0x09eac101u, 0xa602072du, 0x6d96cadcu, 0x4a50189cu, 0x7a1242c8u, 0x04689e95u,
+                                                       0x34c6b38du, 0x26edfa5cu, 0x16375606u, 0xb00b8551u, 0x0348d21cu, 0x599a6f7cu, 0x763cbf9cu, 0x0925c4b8u};
+#endif
 struct FqP {
     static P2B_HD uint32_t p(int i) { return P2B_C(FQ_P, i); }
     static P2B_HD uint32_t one(int i) { return P2B_C(FQ_ONE, i); }
@@ -433,6 +438,86 @@ template <class P> P2B_HD Fp<P> sqr(const Fp<P> &a) {
     return mul(a, a);
 #endif
 }
+
+// ---- wide (unreduced) products and a stand-alone Montgomery reduction: the building blocks of lazy reduction in Fq2, where
+// (a0 + a1 u)(b0 + b1 u) needs three 512-bit products but only TWO reductions (csrc/ec.cuh mul(Fq2, Fq2)).
+#if defined(__CUDA_ARCH__)
+// t[0..15] = a * b.  Same two-accumulator discipline as mont_mul (aligned register pairs for IMAD.WIDE), no reduction rows.
+P2B_D void wide_mul(uint32_t *t, const uint32_t *a, const uint32_t *b) {
+    uint32_t E[18], O[18];
+    row_mul(&E[0], a[0], a[2], a[4], a[6], b[0]);
+    row_mul(&O[1], a[1], a[3], a[5], a[7], b[0]);
+#pragma unroll
+    for (int i = 9; i < 18; i++) E[i] = 0;
+    O[0] = 0;
+#pragma unroll
+    for (int i = 10; i < 18; i++) O[i] = 0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        if (i & 1) {
+            row_mad(&O[i], a[0], a[2], a[4], a[6], b[i]);
+            row_mad(&E[i + 1], a[1], a[3], a[5], a[7], b[i]);
+        } else {
+            row_mad(&E[i], a[0], a[2], a[4], a[6], b[i]);
+            row_mad(&O[i + 1], a[1], a[3], a[5], a[7], b[i]);
+        }
+    }
+    const uint32_t c = add8c(&t[0], &E[0], &O[0], 0);
+    add8c(&t[8], &E[8], &O[8], c);
+}
+// r[0..15] = a + b / a - b over 16 words (callers guarantee no overflow / no negative result)
+P2B_D void add16(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    const uint32_t c = add8c(&r[0], &a[0], &b[0], 0);
+    add8c(&r[8], &a[8], &b[8], c);
+}
+P2B_D void sub16(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    asm("sub.cc.u32 %0, %16, %32;\n\t"
+        "subc.cc.u32 %1, %17, %33;\n\t"
+        "subc.cc.u32 %2, %18, %34;\n\t"
+        "subc.cc.u32 %3, %19, %35;\n\t"
+        "subc.cc.u32 %4, %20, %36;\n\t"
+        "subc.cc.u32 %5, %21, %37;\n\t"
+        "subc.cc.u32 %6, %22, %38;\n\t"
+        "subc.cc.u32 %7, %23, %39;\n\t"
+        "subc.cc.u32 %8, %24, %40;\n\t"
+        "subc.cc.u32 %9, %25, %41;\n\t"
+        "subc.cc.u32 %10, %26, %42;\n\t"
+        "subc.cc.u32 %11, %27, %43;\n\t"
+        "subc.cc.u32 %12, %28, %44;\n\t"
+        "subc.cc.u32 %13, %29, %45;\n\t"
+        "subc.cc.u32 %14, %30, %46;\n\t"
+        "subc.u32 %15, %31, %47;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]),
+          "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]),
+          "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+}
+// r = t / R mod p for t < p * 2^256 (result < 2p before the final conditional subtraction): the reduction phase of mont_sqr
+template <class P> P2B_D void mont_red(uint32_t *r, const uint32_t *t) {
+    uint32_t E[18], O[18];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { E[i] = t[i]; O[i] = 0; }
+#pragma unroll
+    for (int i = 8; i < 18; i++) { E[i] = 0; O[i] = 0; }
+    {
+        const uint32_t m = E[0] * P::inv;
+        row_mad(&E[0], P::p(0), P::p(2), P::p(4), P::p(6), m);
+        row_mad(&O[1], P::p(1), P::p(3), P::p(5), P::p(7), m);
+    }
+    red_step<P>(O, E, 1);
+    red_step<P>(E, O, 2);
+    red_step<P>(O, E, 3);
+    red_step<P>(E, O, 4);
+    red_step<P>(O, E, 5);
+    red_step<P>(E, O, 6);
+    red_step<P>(O, E, 7);
+    uint32_t u[8];
+    add8(u, &E[8], &O[8]);
+    add8(r, u, &t[8]);
+    reduce_once<P>(r);
+}
+#endif
 
 // dedicated squaring wherever the caller asks for it explicitly (device: 100 instead of 128 wide multiplies)
 template <class P> P2B_HD Fp<P> sqr_ded(const Fp<P> &a) {

@@ -44,7 +44,14 @@ static int random_scalars_dev(Ctx *c, uint32_t *d_scalars, size_t n, uint64_t fi
 // Host buffers larger than STREAM_MIN terms are streamed: chunks of up to STREAM_CHUNK terms are copied on the H2D stream into
 // a double-buffered staging area while the previous chunk is sorted and accumulated into the SAME buckets; the bucket
 // reduction runs once at the end.  The sum is unchanged (bucket contents are sums of the same terms).
-static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 24;
+static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 25;
+// growth of the chunk sizes, in eighths (P2B_MSM_STREAM_GROWTH, tuning): a chunk's copy (1.75 ns per G1 term over PCIe 5) hides
+// behind the work on the terms already there (2.8 ns per term) only while the cumulative size grows by <= 1.6x per chunk;
+// plain doubling makes the GPU wait for the copy of every chunk from the fourth on
+static size_t msm_stream_growth8() {
+    static const size_t g = [] { const char *e = getenv("P2B_MSM_STREAM_GROWTH"); long v = e ? atol(e) : 0; return v >= 9 && v <= 32 ? (size_t)v : (size_t)13; }();
+    return g;
+}
 static size_t msm_stream_chunk() {       // P2B_MSM_STREAM_CHUNK=<terms>: test hook to exercise the streamed path at small sizes
     const char *e = getenv("P2B_MSM_STREAM_CHUNK");
     long v = e ? atol(e) : 0;
@@ -83,14 +90,17 @@ static int msm_call(Ctx *c, const MsmCall &a) {
     cudaEvent_t *ev_in = c->ev, *ev_done = c->ev + 2;
     P2B_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
     cudaStream_t CP = streamed ? c->copy_in : c->stream;
-    // chunk sizes double from 1/8 of the maximum (1/8, 1/8, 1/4, 1/2, 1, 1, ..): the GPU starts after a short copy, and
-    // every later copy is hidden behind the work on the terms already on the device
-    size_t off = 0, next = streamed ? (chunk / 8 ? chunk / 8 : 1) : chunk;
+    // chunk sizes grow geometrically from 1/16 of the maximum: the GPU starts after a short copy, and every later copy is
+    // hidden behind the work on the terms already on the device
+    size_t off = 0, next = streamed ? (chunk / 16 ? chunk / 16 : 1) : chunk;
     const int check = ((a.flags & P2B_CHECK_INPUT) ? 1 : 0) | ((a.flags & P2B_REJECT_INFINITY) ? 2 : 0);
     for (size_t ci = 0; off < a.n || ci == 0; ci++) {
         const int b = (int)(ci & 1) % nbuf;
         size_t m = next;
-        if (ci >= 1 && next < chunk) next = next * 2 < chunk ? next * 2 : chunk;
+        if (ci >= 1 && next < chunk) {
+            const size_t grown = next * msm_stream_growth8() / 8 + 1;
+            next = grown < chunk ? grown : chunk;
+        }
         if (m > a.n - off) m = a.n - off;
         const void *d_pts = nullptr, *d_pts_b = nullptr, *d_sc = nullptr;
         if (a.dev) {

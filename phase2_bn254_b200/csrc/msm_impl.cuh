@@ -588,8 +588,8 @@ template <class F> __global__ void __launch_bounds__(256) k_msm_reduce2(const ui
                 dst_base = wrows;
                 dst = kind * 32 + row;
             } else {
-                v = load_xyzz_cg<F>(wrows, kind * 32 + lane);
-                v = select(lane >= nrows, xyzz_infinity<F>(), v);
+                v = xyzz_infinity<F>();
+                if (lane < nrows) v = load_xyzz_cg<F>(wrows, kind * 32 + lane);     // rows beyond nrows were never written
                 weighted = kind == 0;
                 dst_base = sm;
                 dst = kind;
@@ -880,7 +880,12 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
     const int fst = (j.phase & MSM_FIRST) != 0;
     for (uint32_t gi = 0; gi < ngroups; gi++) {
         // the first group is small: its sort is the only one that cannot hide behind an accumulation
-        const uint32_t first_hi = g.nwin / 7 ? g.nwin / 7 : 1;
+        static const int first_env = [] { const char *e = getenv("P2B_MSM_FIRST_GROUP"); return e ? atoi(e) : 0; }();   // tuning hook
+        uint32_t first_hi = g.nwin / 7 ? g.nwin / 7 : 1;
+        // below 2^23 terms two windows do not fill the GPU (one thread per bucket: 2 x 2^14 buckets at 2^20 against 56,832
+        // resident threads) while the group's sort is short anyway: start with a quarter of the windows
+        if (n < ((size_t)1 << 23) && g.nwin >= 8) first_hi = g.nwin / 4;
+        if (first_env > 0 && (uint32_t)first_env < g.nwin) first_hi = (uint32_t)first_env;
         const uint32_t bounds[4] = {0, ngroups == 3 ? first_hi : g.nwin, ngroups == 3 ? (g.nwin + first_hi) / 2 : g.nwin, g.nwin};
         const uint32_t w_lo = bounds[gi], w_hi = ngroups == 3 ? bounds[gi + 1] : g.nwin;
         const uint32_t slot_lo = w_lo * g.nbk, slot_cnt = (w_hi - w_lo) * g.nbk;
