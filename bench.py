@@ -636,11 +636,28 @@ def run_ours(args, rank, world, local_rank):
     # ---- rows that only exist with several GPUs, or whose single-GPU figure is the reference point for them (all ranks take
     #      part; rank 0 keeps the record)
     scale_rows = None
+    scale_failed = False
     if not args.no_extras:
         del pts, sc
         torch.cuda.empty_cache()
         pts = sc = None
-        scale_rows = scaling_extras(args, torch, np, dist, pdist, lib, ctx, rank, world, device, e2e_ms, n)
+        # The headline numbers above are already measured: a failure (or a hang) in these additional rows must not lose them.
+        import signal
+
+        def _alarm(signum, frame):
+            raise TimeoutError("scaling rows exceeded %d s" % args.scaling_rows_timeout)
+
+        signal.signal(signal.SIGALRM, _alarm)
+        signal.alarm(args.scaling_rows_timeout)
+        try:
+            scale_rows = scaling_extras(args, torch, np, dist, pdist, lib, ctx, rank, world, device, e2e_ms, n)
+        except BaseException as exc:       # noqa: BLE001 -- reported in the record; the ranks may be out of step afterwards
+            scale_rows = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            scale_failed = True
+            if rank != 0:
+                os._exit(0)
+        finally:
+            signal.alarm(0)
 
     if rank != 0:
         if world > 1:
@@ -746,6 +763,8 @@ def run_ours(args, rank, world, local_rank):
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
+    if scale_failed:
+        os._exit(0)                       # the other ranks have left (or are stuck in a collective): no barrier to wait in
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -947,6 +966,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--config5-log-n", type=int, default=25, help="scaling rows: log2 of the G1 / G2 MSM terms per GPU (config 5)")
     ap.add_argument("--sharded-transform-size", type=int, default=22, help="scaling rows: log2 of the powers of the sharded transform")
+    ap.add_argument("--scaling-rows-timeout", type=int, default=420, help="seconds after which the scaling rows are abandoned")
     ap.add_argument("--prepare-m", type=int, default=20, help="scaling rows: m of the sharded prepare_phase2")
     ap.add_argument("--max-contribute-log", type=int, default=26, help="scaling rows: largest log2(constraints) of the sharded contribute")
     args = ap.parse_args()

@@ -500,6 +500,7 @@ int p2b_init(int device, p2b_ctx **out) { P2B_RANGE("p2b_init");
               cudaMallocHost(&c->h_err, sizeof(unsigned long long)) == cudaSuccess;
     for (int i = 0; ok && i < 8; i++) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&c->msm_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&c->h2d_ev[i]) == cudaSuccess;
     if (ok) ok = cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), c->stream) == cudaSuccess;
     if (!ok) { p2b_destroy(h); return P2B_ECUDA; }
     *out = h;
@@ -521,6 +522,7 @@ void p2b_destroy(p2b_ctx *h) { P2B_RANGE("p2b_destroy");
     if (c->h_err) cudaFreeHost(c->h_err);
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; i++) if (c->msm_ev[i]) cudaEventDestroy(c->msm_ev[i]);
+    for (int i = 0; i < 2; i++) if (c->h2d_ev[i]) cudaEventDestroy(c->h2d_ev[i]);
     if (c->sort_stream) cudaStreamDestroy(c->sort_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);

@@ -1,4 +1,5 @@
 // msm_g1.cu -- G1 instantiation of the Pippenger MSM kernels and the MSM entry points of the C ABI.
+#include <vector>
 #include "msm_impl.cuh"
 
 namespace p2b {
@@ -90,23 +91,59 @@ static int msm_call(Ctx *c, const MsmCall &a) {
     cudaEvent_t *ev_in = c->ev, *ev_done = c->ev + 2;
     P2B_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
     cudaStream_t CP = streamed ? c->copy_in : c->stream;
-    // chunk sizes grow geometrically from 1/16 of the maximum: the GPU starts after a short copy, and every later copy is
-    // hidden behind the work on the terms already on the device
-    size_t off = 0, next = streamed ? (chunk / 16 ? chunk / 16 : 1) : chunk;
-    const int check = ((a.flags & P2B_CHECK_INPUT) ? 1 : 0) | ((a.flags & P2B_REJECT_INFINITY) ? 2 : 0);
-    for (size_t ci = 0; off < a.n || ci == 0; ci++) {
-        const int b = (int)(ci & 1) % nbuf;
-        size_t m = next;
-        if (ci >= 1 && next < chunk) {
-            const size_t grown = next * msm_stream_growth8() / 8 + 1;
-            next = grown < chunk ? grown : chunk;
+    // Chunk plan.  Sizes grow geometrically from 1/16 of the maximum: the GPU starts after a short copy, and every later copy
+    // is hidden behind the work on the terms already on the device.  When the host link is the slower side (several ranks
+    // pulling from one host: 23 GB/s per rank measured at 8 GPUs against 55 GB/s alone), the run ends with the COMPUTE of the
+    // last chunk, which nothing overlaps -- so the plan then ends with small chunks (1/4, 1/8, 1/8 of the maximum) and uses a
+    // smaller maximum.  The link speed is the one measured on this context's previous streamed call (c->h2d_gbps).
+    std::vector<size_t> plan;
+    if (!streamed) plan.push_back(a.n);
+    else {
+        const double ns_copy = c->h2d_gbps > 0 ? (double)(psz * (a.pair == MSM_PAIR_SEPARATE ? 2 : 1) + (a.scalars ? 32 : 0)) / c->h2d_gbps : 0;
+        const double ns_compute = (a.g2 ? 10.0 : 2.8) * (pair ? 2.0 : 1.0);      // per term, measured (bench.py, one B200)
+        bool copy_bound = ns_copy > 0.85 * ns_compute;
+        if (const char *e = getenv("P2B_MSM_TAIL")) copy_bound = atoi(e) != 0;   // tuning / test hook
+        const size_t cap = copy_bound && !ov ? chunk / 2 : chunk;
+        const size_t tail[3] = {cap / 4, cap / 8, cap / 8};
+        const size_t tail_total = copy_bound ? tail[0] + tail[1] + tail[2] : 0;
+        size_t rem = a.n, next = chunk / 16 ? chunk / 16 : 1;
+        while (rem > tail_total) {
+            size_t m = next < rem - tail_total ? next : rem - tail_total;
+            plan.push_back(m);
+            rem -= m;
+            if (plan.size() >= 2 && next < cap) {
+                const size_t grown = next * msm_stream_growth8() / 8 + 1;
+                next = grown < cap ? grown : cap;
+            }
         }
-        if (m > a.n - off) m = a.n - off;
+        for (int t = 0; t < 3 && rem; t++) {
+            const size_t m = t == 2 || tail[t] > rem ? rem : tail[t];
+            plan.push_back(m);
+            rem -= m;
+        }
+    }
+    // link-speed probe of the previous streamed call
+    if (c->h2d_probe_bytes && cudaEventQuery(c->h2d_ev[1]) == cudaSuccess) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->h2d_ev[0], c->h2d_ev[1]) == cudaSuccess && ms > 0) c->h2d_gbps = (double)c->h2d_probe_bytes / (ms * 1e6);
+        c->h2d_probe_bytes = 0;
+    }
+    size_t probe_ci = plan.size();
+    if (streamed && !a.dev) {            // time the copies of the largest chunk
+        probe_ci = 0;
+        for (size_t i = 1; i < plan.size(); i++) if (plan[i] > plan[probe_ci]) probe_ci = i;
+    }
+    size_t off = 0;
+    const int check = ((a.flags & P2B_CHECK_INPUT) ? 1 : 0) | ((a.flags & P2B_REJECT_INFINITY) ? 2 : 0);
+    for (size_t ci = 0; ci < plan.size(); ci++) {
+        const int b = (int)(ci & 1) % nbuf;
+        const size_t m = plan[ci];
         const void *d_pts = nullptr, *d_pts_b = nullptr, *d_sc = nullptr;
         if (a.dev) {
             d_pts = a.points; d_pts_b = a.points_b; d_sc = a.scalars;
         } else {
             if (streamed) P2B_CUDA(c, cudaStreamWaitEvent(CP, ci >= 2 ? ev_done[b] : c->ev[6], 0));
+            if (ci == probe_ci) P2B_CUDA(c, cudaEventRecord(c->h2d_ev[0], CP));
             char *st = (char *)c->stage_in[b].p;
             if ((m + extra) && (rc = io_h2d(c, st, a.points + off * isz, (m + extra) * isz, CP))) return rc;
             d_pts = st;
@@ -118,6 +155,10 @@ static int msm_call(Ctx *c, const MsmCall &a) {
                 if (m && (rc = io_h2d(c, st + off_s, a.scalars + off * 32, m * 32, CP))) return rc;
                 d_sc = st + off_s;
             }
+        }
+        if (ci == probe_ci && !a.dev) {
+            P2B_CUDA(c, cudaEventRecord(c->h2d_ev[1], CP));
+            c->h2d_probe_bytes = (m + extra) * isz + (a.pair == MSM_PAIR_SEPARATE ? m * isz : 0) + (a.scalars ? m * 32 : 0);
         }
         if (!a.scalars) {
             char *st = (char *)c->stage_in[b].p;
@@ -154,7 +195,6 @@ static int msm_call(Ctx *c, const MsmCall &a) {
         if ((rc = msm_typed_any(c, a.g2, j))) return rc;
         if (streamed) P2B_CUDA(c, cudaEventRecord(ev_done[b], c->stream));
         off += m;
-        if (off >= a.n) break;
     }
     P2B_CUDA(c, cudaMemcpyAsync(a.out_a, d_out, psz, cudaMemcpyDeviceToHost, c->stream));
     if (pair) P2B_CUDA(c, cudaMemcpyAsync(a.out_b, d_out + psz / 4, psz, cudaMemcpyDeviceToHost, c->stream));

@@ -25,6 +25,9 @@ struct Ctx {
     cudaStream_t copy_out = nullptr;     // D2H
     cudaStream_t sort_stream = nullptr;  // MSM counting sort (high priority), overlapped with the bucket accumulation
     cudaEvent_t msm_ev[4] = {};
+    cudaEvent_t h2d_ev[2] = {};          // timing events around the copies of one streamed MSM chunk (link-speed probe)
+    size_t h2d_probe_bytes = 0;
+    double h2d_gbps = 0;                 // host -> device rate seen by the previous streamed call (0: not measured yet)
     int sm_count = 148;
     std::string last_error;
     uint64_t err_index = 0;

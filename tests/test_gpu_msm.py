@@ -130,3 +130,17 @@ def test_msm_skewed_scalars(ctx, oracle, group, monkeypatch):
     monkeypatch.setenv("P2B_MSM_STREAM_CHUNK", "1000")          # streamed chunks continue the same buckets
     assert ctx.msm(group, pts, sc) == exp
     assert ctx.msm(group, pts, k * n) == oracle.msm(group, pts, k * n, threads=8)
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_msm_streamed_copy_bound_plan(ctx, oracle, group, monkeypatch):
+    """The chunk plan used when the host link is the slower side (small chunks at the end, P2B_MSM_TAIL forces it): same sum."""
+    n = 3000
+    pts = random_points(oracle, group, n, seed=171)
+    sc = random_scalars(n, seed=172)
+    exp = oracle.msm(group, pts, sc, threads=8)
+    for tail in ("1", "0"):
+        monkeypatch.setenv("P2B_MSM_TAIL", tail)
+        for chunk in (512, 1000, 2999):
+            monkeypatch.setenv("P2B_MSM_STREAM_CHUNK", str(chunk))
+            assert ctx.msm(group, pts, sc) == exp, (tail, chunk)
