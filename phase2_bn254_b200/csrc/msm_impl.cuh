@@ -325,10 +325,28 @@ struct MsmHeavy {
     uint32_t *partials;   // one XYZZ per item
     uint32_t seg, chunk, cap_items, cap_buckets;
 };
+// A gathered point is 64 B (G1) / 128 B (G2) of a random 128-byte line: by default the miss fills the whole line (124 B of DRAM
+// reads per 64-byte G1 gather measured).  The L2::64B prefetch-size qualifier asks for the touched half only.
+#ifndef P2B_GATHER_L2_HINT
+#define P2B_GATHER_L2_HINT 1
+#endif
+template <int NW> __device__ __forceinline__ void ldw_gather(uint32_t *dst, const uint32_t *src) {
+#if P2B_GATHER_L2_HINT
+    if constexpr (NW == 16) {
+#pragma unroll
+        for (int i = 0; i < NW / 4; i++)
+            asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(dst[4 * i]), "=r"(dst[4 * i + 1]), "=r"(dst[4 * i + 2]), "=r"(dst[4 * i + 3])
+                         : "l"(src + 4 * i));
+        return;
+    }
+#endif
+    ldw<NW>(dst, src);
+}
 template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc, const uint32_t *aff, uint32_t ent) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
     uint32_t w[WU];
-    ldw<WU>(w, aff + (size_t)(ent >> 1) * WU);
+    ldw_gather<WU>(w, aff + (size_t)(ent >> 1) * WU);
     uint32_t any = 0;
 #pragma unroll
     for (int j = 0; j < WU; j++) any |= w[j];
@@ -348,7 +366,7 @@ template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc
 //   3  variant 1 at 4 blocks per SM (<= 128 registers)
 template <class F, int VARIANT> struct AccBounds { static constexpr int MIN_BLOCKS = VARIANT == 3 ? 4 : (VARIANT == 0 ? 1 : 3); };
 template <class F> __device__ __forceinline__ void load_point_words(uint32_t *w, const uint32_t *aff, uint32_t ent) {
-    ldw<Wire<F>::WORDS_UNCOMPRESSED>(w, aff + (size_t)(ent >> 1) * Wire<F>::WORDS_UNCOMPRESSED);
+    ldw_gather<Wire<F>::WORDS_UNCOMPRESSED>(w, aff + (size_t)(ent >> 1) * Wire<F>::WORDS_UNCOMPRESSED);
 }
 template <class F, bool SQ> __device__ __forceinline__ void accumulate_words(Xyzz<F> &acc, const uint32_t *w, uint32_t ent) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
