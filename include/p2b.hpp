@@ -13,6 +13,7 @@
 //   p2b::phase2::MPCParameters::{read, write, contribute}
 //                                                   phase2/src/parameters.rs:414-522, 663-703
 //   p2b::bellman::{dense_multiexp, EvaluationDomain}   bellman/src/multiexp.rs:361-475, domain.rs:52-205
+//   p2b::bellman::{merge_pairs_g1, power_pairs_g1/g2}  powersoftau/src/utils.rs:112-135 (one pass on the GPU)
 //
 // Field elements cross as 32-byte big-endian canonical values (`into_repr().write_be()`), points as the wire encodings
 // of pairing/src/bn256/ec.rs; maps are (pointer, length) views of the mmaps.
@@ -259,6 +260,31 @@ inline std::array<uint8_t, 128> dense_multiexp_g2(const Context &ctx, const uint
     std::array<uint8_t, 128> out;
     ctx.check(p2b_g2_msm(ctx.get(), bases, exponents, n, out.data()));
     return out;
+}
+
+// merge_pairs / power_pairs of the verifiers (powersoftau/src/utils.rs:112-135, phase2/src/utils.rs:59-105): the random linear
+// combination (sum rho_i v1_i, sum rho_i v2_i) in ONE pass on the GPU.  The coefficients are generated on the device from `seed`
+// (32 bytes of OS entropy; ChaCha20 keystream) -- the reference draws Fr::rand(thread_rng()) per element.  `enc` is the encoding
+// the points have in the file (compressed chunks are decompressed on the device); flags: P2B_CHECK_INPUT, P2B_REJECT_INFINITY.
+struct PointPairG1 { std::array<uint8_t, 64> s, sx; };
+struct PointPairG2 { std::array<uint8_t, 128> s, sx; };
+inline PointPairG1 merge_pairs_g1(const Context &ctx, const uint8_t *v1, const uint8_t *v2, size_t n, const uint8_t seed[32],
+                                  uint32_t scalar_bits = 253, int enc = P2B_ENC_UNCOMPRESSED, int flags = 0) {
+    PointPairG1 r;
+    ctx.check(p2b_g1_msm_pair(ctx.get(), v1, v2, nullptr, n, seed, scalar_bits, enc, flags, r.s.data(), r.sx.data()));
+    return r;
+}
+inline PointPairG1 power_pairs_g1(const Context &ctx, const uint8_t *v, size_t n_points, const uint8_t seed[32], uint32_t scalar_bits = 253,
+                                  int enc = P2B_ENC_UNCOMPRESSED, int flags = 0) {
+    PointPairG1 r;
+    ctx.check(p2b_g1_power_pairs(ctx.get(), v, n_points, nullptr, seed, scalar_bits, enc, flags, r.s.data(), r.sx.data()));
+    return r;
+}
+inline PointPairG2 power_pairs_g2(const Context &ctx, const uint8_t *v, size_t n_points, const uint8_t seed[32], uint32_t scalar_bits = 253,
+                                  int enc = P2B_ENC_UNCOMPRESSED, int flags = 0) {
+    PointPairG2 r;
+    ctx.check(p2b_g2_power_pairs(ctx.get(), v, n_points, nullptr, seed, scalar_bits, enc, flags, r.s.data(), r.sx.data()));
+    return r;
 }
 
 // EvaluationDomain over Fr (domain.rs:52-205): coefficients padded with zeros to the next power of two.

@@ -56,6 +56,15 @@ int main(int argc, char **argv) {
         const size_t n = sc.size() / 32;
         auto sum = bellman::dense_multiexp_g1(ctx, next.data() + 64, sc.data(), n);
         spit(dir + "/msm", sum.data(), sum.size());
+        // the verifier's power_pairs over the COMPRESSED tau_g1 section of the response, coefficients from a fixed seed
+        {
+            uint8_t seed[32];
+            for (int i = 0; i < 32; i++) seed[i] = (uint8_t)(7 * i + 3);
+            auto pp = bellman::power_pairs_g1(ctx, response.data() + 64, n, seed, 253, P2B_ENC_COMPRESSED, P2B_REJECT_INFINITY);
+            std::vector<uint8_t> both(pp.s.begin(), pp.s.end());
+            both.insert(both.end(), pp.sx.begin(), pp.sx.end());
+            spit(dir + "/power_pairs", both.data(), both.size());
+        }
         std::vector<Scalar> coeffs(n);
         for (size_t i = 0; i < n; i++) memcpy(coeffs[i].data(), &sc[32 * i], 32);
         auto dom = bellman::EvaluationDomain::from_coeffs(coeffs);

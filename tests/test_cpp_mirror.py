@@ -47,6 +47,9 @@ def test_cpp_mirror_matches_oracle(exe, tmp_path, oracle):
     assert rd("new_challenge")[64:] == nxt[64:]
     assert rd("msm") == oracle.msm(0, nxt[64:64 + 64 * n], sc, threads=4)
     assert rd("fft") == oracle.fr_fft(sc, threads=2) and rd("fft_roundtrip") == sc
+    from util import device_scalars
+    rho = device_scalars(bytes((7 * i + 3) & 0xff for i in range(32)), n - 1, 253)
+    assert rd("power_pairs") == oracle.msm(0, nxt[64:64 + 64 * (n - 1)], rho, threads=4) + oracle.msm(0, nxt[128:64 + 64 * n], rho, threads=4)
     from phase2_bn254_b200 import lib
     import numpy as np
     c = lib.Context(0)
