@@ -56,3 +56,18 @@ def test_frobenius_tables(oracle, name, k, mult, count):
     got = xi_pow_chain(oracle, k, mult, count)
     for i in range(count):
         assert got[i] == ref[i], "%s[%d] (%s)" % (name, i, KAT[name]["lines"])
+
+
+def test_generator_roots_as_the_reference_asserts(oracle):
+    """pairing/src/bn256/ec.rs:1512-1539 `g2_generator_on_curve`: y = sqrt(x^3 + 3/xi) at the generator's x, the SMALLER root in the
+    Fq2 order (c1 first), IS the hard-coded generator's y (fq.rs:60-83) -- a reference-asserted value for the oracle's Fq2 sqrt
+    (fq2.rs:206-262) and ordering; ec.rs:1013-1051 `g1_generator`: the smaller root at x = 1 is y = 2."""
+    from util import G1_GEN, G2_GEN
+    for group, gen in ((0, G1_GEN), (1, G2_GEN)):
+        comp = oracle.point_recode(group, gen, 0, 1)
+        assert comp[0] & 0x80 == 0                                   # "y < negy": the generator carries the smaller root
+        assert comp == gen[: len(gen) // 2]
+        assert oracle.point_recode(group, comp, 1, 0) == gen         # sqrt + root selection reproduce the hard-coded y
+        flipped = bytes([comp[0] | 0x80]) + comp[1:]
+        neg = oracle.point_recode(group, flipped, 1, 0)
+        assert neg[: len(gen) // 2] == gen[: len(gen) // 2] and neg != gen
