@@ -23,6 +23,7 @@
 #include <cstring>
 #include "codec.cuh"
 #include "xyzz.cuh"
+#include "msm_g2x2.cuh"
 #include "p2b_internal.h"
 
 #ifndef P2B_ACC_DEFAULT_VARIANT
@@ -364,6 +365,7 @@ template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc
 //      latency that 3 warps per scheduler do not always cover)
 //   2  variant 1 + the two squarings of the mixed add on the dedicated squaring routine
 //   3  variant 1 at 4 blocks per SM (<= 128 registers)
+//   5  the plain loop of variant 0 at 3 blocks per SM (<= 168 registers): a G2 tuning variant (P2B_ACC_VARIANT_G2)
 template <class F, int VARIANT> struct AccBounds { static constexpr int MIN_BLOCKS = VARIANT == 3 ? 4 : (VARIANT == 0 ? 1 : 3); };
 template <class F> __device__ __forceinline__ void load_point_words(uint32_t *w, const uint32_t *aff, uint32_t ent) {
     ldw_gather<Wire<F>::WORDS_UNCOMPRESSED>(w, aff + (size_t)(ent >> 1) * Wire<F>::WORDS_UNCOMPRESSED);
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(128, AccBounds<F, VARIANT>::MIN_BLOCKS) k_msm_
             acc = load_xyzz<F>(buckets, gb);
         }
         const uint32_t mine = hi - lo > hv.seg ? lo + hv.seg : hi;
-        if constexpr (VARIANT == 0) {
+        if constexpr (VARIANT == 0 || VARIANT == 5) {
 #pragma unroll 1
             for (uint32_t e = lo; e < mine; e++) accumulate_entry<F>(acc, aff, __ldg(sorted + e));
         } else {
@@ -432,6 +434,61 @@ __global__ void __launch_bounds__(128, AccBounds<F, VARIANT>::MIN_BLOCKS) k_msm_
             } else report_err(err, gb, P2B_ECUDA, 0);          // cannot happen: the capacities cover the worst case
         }
     }
+}
+
+// G2 with two lanes per bucket (msm_g2x2.cuh): lane pair (2j, 2j+1) of a block owns one bucket; each lane loads, keeps and
+// stores its own component of every Fq2 coordinate.  SETS = 2 walks the list twice, once per bucket set of the pair mode.
+#ifndef P2B_G2X2_MIN_BLOCKS
+#define P2B_G2X2_MIN_BLOCKS 3
+#endif
+template <int SETS>
+__global__ void __launch_bounds__(128, P2B_G2X2_MIN_BLOCKS) k_msm_accumulate_g2x2(const uint32_t *aff_a, const uint32_t *aff_b, const uint32_t *offsets,
+                                                                                  const uint32_t *sorted, uint32_t *buckets_a, uint32_t *buckets_b,
+                                                                                  int first, uint32_t slot_lo, uint32_t slot_cnt, MsmHeavy hv,
+                                                                                  unsigned long long *err, const uint32_t *perm) {
+#if defined(__CUDA_ARCH__)
+    const int lane = threadIdx.x & 31, odd = lane & 1;
+    const unsigned pm = 3u << (lane & ~1);
+    const uint32_t npairs = gridDim.x * (blockDim.x >> 1);
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 1; t < slot_cnt; t += npairs) {
+        const uint32_t idx = perm[t];
+        const uint32_t gb = slot_lo + idx;
+        const uint32_t lo = offsets[idx], hi = offsets[idx + 1];
+        if (!first && lo == hi) continue;
+        const uint32_t mine = SETS == 1 && hi - lo > hv.seg ? lo + hv.seg : hi;      // pair mode walks whole buckets (see k_msm_accumulate_pair)
+#pragma unroll 1
+        for (int set = 0; set < SETS; set++) {
+            const uint32_t *aff = set ? aff_b : aff_a;
+            uint32_t *bk = set ? buckets_b : buckets_a;
+            XyzzHalf acc;
+            acc.x = fp_zero<FqP>(); acc.y = fp_zero<FqP>(); acc.zz = fp_zero<FqP>(); acc.zzz = fp_zero<FqP>();
+            if (!first) acc = load_xyzz_half(bk, gb, odd);
+#pragma unroll 1
+            for (uint32_t e = lo; e < mine; e++) {
+                const uint32_t ent = __ldg(sorted + e);
+                const uint4 *src = reinterpret_cast<const uint4 *>(aff + (size_t)(ent >> 1) * 32 + 8 * odd);   // x.c0 x.c1 y.c0 y.c1, 8 words each
+                const uint4 x0 = __ldg(src), x1 = __ldg(src + 1), y0 = __ldg(src + 4), y1 = __ldg(src + 5);
+                Fq qx, qy;
+                qx.l[0] = x0.x; qx.l[1] = x0.y; qx.l[2] = x0.z; qx.l[3] = x0.w; qx.l[4] = x1.x; qx.l[5] = x1.y; qx.l[6] = x1.z; qx.l[7] = x1.w;
+                qy.l[0] = y0.x; qy.l[1] = y0.y; qy.l[2] = y0.z; qy.l[3] = y0.w; qy.l[4] = y1.x; qy.l[5] = y1.y; qy.l[6] = y1.z; qy.l[7] = y1.w;
+                if (!either(!(is_zero(qx) & is_zero(qy)), pm)) continue;            // all-zero = point at infinity: contributes nothing
+                h2_madd(acc, qx, qy, (ent & 1u) != 0, odd != 0, pm);
+            }
+            store_xyzz_half(bk, gb, odd, acc);
+        }
+        if (SETS == 1 && mine < hi && !odd) {                 // overflow: hand the tail to k_msm_heavy (one lane of the pair)
+            const uint32_t nit = (hi - mine + hv.chunk - 1) / hv.chunk;
+            const uint32_t fi = atomicAdd(&hv.counters[0], nit), hb = atomicAdd(&hv.counters[1], 1u);
+            if (fi + nit <= hv.cap_items && hb < hv.cap_buckets) {
+                for (uint32_t k = 0; k < nit; k++) {
+                    const uint32_t a = mine + k * hv.chunk, b = hi - a > hv.chunk ? a + hv.chunk : hi;
+                    hv.items[fi + k] = make_uint4(gb, a, b, 0u);
+                }
+                hv.hbuckets[hb] = make_uint4(gb, fi, nit, 0u);
+            } else report_err(err, gb, P2B_ECUDA, 0);
+        }
+    }
+#endif
 }
 
 // Pair mode: ONE sorted list of (term, sign) entries drives TWO bucket sets -- sum k_i A_i and sum k_i B_i for two point
@@ -930,6 +987,12 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
         const int agrid = (int)((slot_cnt + 127) / 128);
         prof_begin(c, P2B_PROF_MSM_ACCUMULATE);
         if (pair) {
+            static const int pair_g2 = [] { const char *e = getenv("P2B_ACC_VARIANT_G2"); return e ? atoi(e) : 0; }();
+            if (W == 16 && pair_g2 != 9) {
+                MsmHeavy none = hv;
+                k_msm_accumulate_g2x2<2><<<(int)((slot_cnt + 63) / 64), 128, 0, C>>>(aff, aff_b, offs, sorted, buckets, buckets_b, fst, slot_lo, slot_cnt,
+                                                                                      none, c->d_err, perm + slot_lo);
+            } else
             k_msm_accumulate_pair<F><<<agrid, 128, 0, C>>>(aff, aff_b, offs, sorted, buckets, buckets_b, fst, slot_lo, slot_cnt, perm + slot_lo);
             prof_end(c, P2B_PROF_MSM_ACCUMULATE, 1);
             c->launches += 9;
@@ -939,7 +1002,17 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
         {
             static const int variant = [] { const char *e = getenv("P2B_ACC_VARIANT"); return e ? atoi(e) : P2B_ACC_DEFAULT_VARIANT; }();
 #define P2B_ACC_LAUNCH(V) k_msm_accumulate<F, V><<<agrid, 128, 0, C>>>(aff, offs, sorted, g, buckets, fst, slot_lo, slot_cnt, hv, c->d_err, perm + slot_lo)
-            if (W != 8 || variant == 0) P2B_ACC_LAUNCH(0);      // G2 (255 registers already) keeps the plain loop
+            static const int variant_g2 = [] { const char *e = getenv("P2B_ACC_VARIANT_G2"); return e ? atoi(e) : 0; }();
+            if (W != 8) {                                       // G2: two lanes per bucket; the one-thread variants stay selectable
+                if constexpr (W != 8) {
+                    if (variant_g2 == 5) P2B_ACC_LAUNCH(5);
+                    else if (variant_g2 == 1) P2B_ACC_LAUNCH(1);
+                    else if (variant_g2 == 9) P2B_ACC_LAUNCH(0);
+                    else k_msm_accumulate_g2x2<1><<<(int)((slot_cnt + 63) / 64), 128, 0, C>>>(aff, aff, offs, sorted, buckets, buckets, fst, slot_lo,
+                                                                                                slot_cnt, hv, c->d_err, perm + slot_lo);
+                }
+            }
+            else if (variant == 0) P2B_ACC_LAUNCH(0);
             else if (variant == 1) { if constexpr (W == 8) P2B_ACC_LAUNCH(1); }
             else if (variant == 2) { if constexpr (W == 8) P2B_ACC_LAUNCH(2); }
             else { if constexpr (W == 8) P2B_ACC_LAUNCH(3); }
