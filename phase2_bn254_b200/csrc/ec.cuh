@@ -115,6 +115,10 @@ template <class F> P2B_HD Jac<F> select(bool c, const Jac<F> &b, const Jac<F> &a
     Jac<F> r; r.x = select(c, b.x, a.x); r.y = select(c, b.y, a.y); r.z = select(c, b.z, a.z); return r;
 }
 
+// a b - c d: for Fq one fused two-product Montgomery multiplication (fp.cuh mont_mul2: 200 instead of 272 wide multiplies)
+template <class F> P2B_HD F mul_sub2(const F &a, const F &b, const F &c, const F &d) { return sub(mul(a, b), mul(c, d)); }
+template <> P2B_HD Fq mul_sub2<Fq>(const Fq &a, const Fq &b, const Fq &c, const Fq &d) { return mul2_add(a, b, c, neg(d)); }
+
 // dbl-2009-l: 2M + 5S.  z == 0 stays 0.
 template <class F> P2B_HD Jac<F> jac_dbl(const Jac<F> &p) {
     F a = sqr(p.x);
@@ -159,7 +163,7 @@ template <class F> P2B_HD Jac<F> jac_madd(const Jac<F> &p, const Aff<F> &q) {
     F v = mul(p.x, i);
     Jac<F> r;
     r.x = sub(sub(sub(sqr(rr), j), v), v);
-    r.y = sub(mul(rr, sub(v, r.x)), dbl(mul(p.y, j)));
+    r.y = mul_sub2(rr, sub(v, r.x), p.y, dbl(j));
     r.z = sub(sub(sqr(add(p.z, h)), z1z1), hh);
     bool p_inf = is_zero(p.z);
     bool same = is_zero(h) & is_zero(rr) & !p_inf;
@@ -183,7 +187,7 @@ template <class F> P2B_HD Jac<F> jac_add(const Jac<F> &p, const Jac<F> &q) {
     F v = mul(u1, i);
     Jac<F> r;
     r.x = sub(sub(sub(sqr(rr), j), v), v);
-    r.y = sub(mul(rr, sub(v, r.x)), dbl(mul(s1, j)));
+    r.y = mul_sub2(rr, sub(v, r.x), s1, dbl(j));
     r.z = mul(sub(sub(sqr(add(p.z, q.z)), z1z1), z2z2), h);
     bool p_inf = is_zero(p.z), q_inf = is_zero(q.z);
     bool same = is_zero(h) & is_zero(rr) & !p_inf & !q_inf;

@@ -566,6 +566,17 @@ template <class P> P2B_HD Fp<P> sqr_ded(const Fp<P> &a) {
 #endif
 }
 
+// a * b + c * d with one reduction (device: mont_mul2, 200 instead of 272 wide multiplies)
+template <class P> P2B_HD Fp<P> mul2_add(const Fp<P> &a, const Fp<P> &b, const Fp<P> &c, const Fp<P> &d) {
+#if defined(__CUDA_ARCH__)
+    Fp<P> r;
+    mont_mul2<P>(r.l, a.l, b.l, c.l, d.l);
+    return r;
+#else
+    return add(mul(a, b), mul(c, d));
+#endif
+}
+
 // canonical <-> Montgomery
 template <class P> P2B_HD Fp<P> to_mont(const Fp<P> &a) {
     Fp<P> r2;

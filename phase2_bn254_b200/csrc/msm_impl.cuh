@@ -27,7 +27,7 @@
 #include "p2b_internal.h"
 
 #ifndef P2B_ACC_DEFAULT_VARIANT
-#define P2B_ACC_DEFAULT_VARIANT 2
+#define P2B_ACC_DEFAULT_VARIANT 4
 #endif
 
 namespace p2b {
@@ -326,6 +326,10 @@ struct MsmHeavy {
     uint32_t *partials;   // one XYZZ per item
     uint32_t seg, chunk, cap_items, cap_buckets;
 };
+template <class F> __device__ __forceinline__ Xyzz<F> madd_fused_if_g1(const Xyzz<F> &acc, const Aff<F> &q) {
+    if constexpr (FieldTraits<F>::WORDS == 8) return xyzz_madd_fused(acc, q);
+    else return xyzz_madd_sq(acc, q);
+}
 // A gathered point is 64 B (G1) / 128 B (G2) of a random 128-byte line: by default the miss fills the whole line (124 B of DRAM
 // reads per 64-byte G1 gather measured).  The L2::64B prefetch-size qualifier asks for the touched half only.
 #ifndef P2B_GATHER_L2_HINT
@@ -356,7 +360,7 @@ template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc
 #pragma unroll
     for (int j = 0; j < W; j++) { set_word(q.x, j, w[j]); set_word(q.y, j, w[W + j]); }
     q.y = cneg(q.y, (ent & 1u) != 0);
-    acc = xyzz_madd(acc, q);
+    acc = madd_fused_if_g1(acc, q);
 }
 // Bucket accumulation, one thread per bucket.  VARIANT (tuning, selected at run time by P2B_ACC_VARIANT; all give the same sums):
 //   0  the round-1 loop: entry -> gather -> mixed add, nothing in flight across iterations
@@ -365,12 +369,13 @@ template <class F> __device__ __forceinline__ void accumulate_entry(Xyzz<F> &acc
 //      latency that 3 warps per scheduler do not always cover)
 //   2  variant 1 + the two squarings of the mixed add on the dedicated squaring routine
 //   3  variant 1 at 4 blocks per SM (<= 128 registers)
+//   4  variant 2 + Y3 as one fused two-product multiplication (mont_mul2)
 //   5  the plain loop of variant 0 at 3 blocks per SM (<= 168 registers): a G2 tuning variant (P2B_ACC_VARIANT_G2)
 template <class F, int VARIANT> struct AccBounds { static constexpr int MIN_BLOCKS = VARIANT == 3 ? 4 : (VARIANT == 0 ? 1 : 3); };
 template <class F> __device__ __forceinline__ void load_point_words(uint32_t *w, const uint32_t *aff, uint32_t ent) {
     ldw_gather<Wire<F>::WORDS_UNCOMPRESSED>(w, aff + (size_t)(ent >> 1) * Wire<F>::WORDS_UNCOMPRESSED);
 }
-template <class F, bool SQ> __device__ __forceinline__ void accumulate_words(Xyzz<F> &acc, const uint32_t *w, uint32_t ent) {
+template <class F, int SQ> __device__ __forceinline__ void accumulate_words(Xyzz<F> &acc, const uint32_t *w, uint32_t ent) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED, W = FieldTraits<F>::WORDS;
     uint32_t any = 0;
 #pragma unroll
@@ -380,7 +385,7 @@ template <class F, bool SQ> __device__ __forceinline__ void accumulate_words(Xyz
 #pragma unroll
     for (int j = 0; j < W; j++) { set_word(q.x, j, w[j]); set_word(q.y, j, w[W + j]); }
     q.y = cneg(q.y, (ent & 1u) != 0);
-    acc = SQ ? xyzz_madd_sq(acc, q) : xyzz_madd(acc, q);
+    acc = SQ == 2 ? madd_fused_if_g1(acc, q) : (SQ == 1 ? xyzz_madd_sq(acc, q) : xyzz_madd(acc, q));
 }
 template <class F, int VARIANT>
 __global__ void __launch_bounds__(128, AccBounds<F, VARIANT>::MIN_BLOCKS) k_msm_accumulate(const uint32_t *aff, const uint32_t *offsets, const uint32_t *sorted,
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(128, AccBounds<F, VARIANT>::MIN_BLOCKS) k_msm_
                     uint32_t wn[WU];
                     const uint32_t ent2 = e + 2 < mine ? __ldg(sorted + e + 2) : 0u;
                     if (e + 1 < mine) load_point_words<F>(wn, aff, ent1);      // in flight during the mixed add below
-                    accumulate_words<F, VARIANT == 2>(acc, w, ent);
+                    accumulate_words<F, VARIANT == 4 ? 2 : (VARIANT == 2 ? 1 : 0)>(acc, w, ent);
 #pragma unroll
                     for (int j = 0; j < WU; j++) w[j] = wn[j];
                     ent = ent1;
@@ -1015,6 +1020,7 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
             else if (variant == 0) P2B_ACC_LAUNCH(0);
             else if (variant == 1) { if constexpr (W == 8) P2B_ACC_LAUNCH(1); }
             else if (variant == 2) { if constexpr (W == 8) P2B_ACC_LAUNCH(2); }
+            else if (variant == 4) { if constexpr (W == 8) P2B_ACC_LAUNCH(4); }
             else { if constexpr (W == 8) P2B_ACC_LAUNCH(3); }
 #undef P2B_ACC_LAUNCH
         }

@@ -63,6 +63,20 @@ template <class F> P2B_HD Xyzz<F> xyzz_madd_sq(const Xyzz<F> &p, const Aff<F> &q
     Xyzz<F> qa; qa.x = q.x; qa.y = q.y; qa.zz = FieldTraits<F>::one(); qa.zzz = FieldTraits<F>::one();
     return select(p_inf, qa, r);
 }
+// variant of xyzz_madd_sq with Y3 = R (Q - X3) + Y1 (-PPP) as ONE two-product Montgomery multiplication (G1 tuning variant)
+P2B_HD Xyzz<Fq> xyzz_madd_fused(const Xyzz<Fq> &p, const Aff<Fq> &q) {
+    Fq u2 = mul(q.x, p.zz), s2 = mul(q.y, p.zzz);
+    Fq pp_ = sub(u2, p.x), rr = sub(s2, p.y);
+    Fq pp = sqr_ded(pp_), ppp = mul(pp_, pp), qq = mul(p.x, pp);
+    Xyzz<Fq> r;
+    r.x = sub(sub(sub(sqr_ded(rr), ppp), qq), qq);
+    r.y = mul2_add(rr, sub(qq, r.x), p.y, neg(ppp));
+    r.zz = mul(p.zz, pp); r.zzz = mul(p.zzz, ppp);
+    bool p_inf = is_zero(p.zz);
+    if (!p_inf & is_zero(pp_) & is_zero(rr)) r = xyzz_dbl_aff(q);
+    Xyzz<Fq> qa; qa.x = q.x; qa.y = q.y; qa.zz = FieldTraits<Fq>::one(); qa.zzz = FieldTraits<Fq>::one();
+    return select(p_inf, qa, r);
+}
 // add-2008-s, complete
 template <class F> P2B_HD Xyzz<F> xyzz_add(const Xyzz<F> &p, const Xyzz<F> &q) {
     F u1 = mul(p.x, q.zz), u2 = mul(q.x, p.zz), s1 = mul(p.y, q.zzz), s2 = mul(q.y, p.zzz);
