@@ -134,6 +134,21 @@ template <class F> P2B_HD Jac<F> jac_dbl(const Jac<F> &p) {
     r.y = sub(mul(e, sub(d, r.x)), c8);
     return r;
 }
+// The same doubling for Fq with the fused two-product multiplication: D = 4 X B needs no C, and Y3 = E (D - X3) - (8 B) B is ONE
+// mont_mul2 -- 5 multiplications + 1 fused (880 wide multiplies) instead of 7 multiplications (952).  (Not for Fq2, where the
+// squaring (X + B)^2 is cheaper than the product X B.)
+P2B_HD Jac<Fq> jac_dbl(const Jac<Fq> &p) {
+    Fq a = sqr(p.x);
+    Fq b = sqr(p.y);
+    Fq d = dbl(dbl(mul(p.x, b)));
+    Fq e = add(dbl(a), a);
+    Fq f = sqr(e);
+    Jac<Fq> r;
+    r.z = dbl(mul(p.y, p.z));
+    r.x = sub(sub(f, d), d);
+    r.y = mul_sub2(e, sub(d, r.x), dbl(dbl(dbl(b))), b);
+    return r;
+}
 // doubling of an affine point (Z1 = 1): mdbl-2007-bl shape, 1M + 5S
 template <class F> P2B_HD Jac<F> aff_dbl(const Aff<F> &p) {
     F a = sqr(p.x);
