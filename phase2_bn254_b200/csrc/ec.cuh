@@ -29,7 +29,13 @@ P2B_HD Fq2 select(bool c, const Fq2 &b, const Fq2 &a) {
 P2B_HD Fq2 cneg(const Fq2 &a, bool c) { return select(c, neg(a), a); }
 // (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u   (fq2.rs:167-180)
 P2B_HD Fq2 mul(const Fq2 &a, const Fq2 &b) {
-#if defined(__CUDA_ARCH__) && defined(P2B_FQ2_LAZY)
+#if defined(__CUDA_ARCH__) && defined(P2B_FQ2_SCHOOLBOOK)
+    // schoolbook with two fused two-product multiplications (400 wide multiplies, no 512-bit temporaries): tuning variant
+    Fq2 r;
+    mont_mul2<FqP>(r.c0.l, a.c0.l, b.c0.l, a.c1.l, neg(b.c1).l);
+    mont_mul2<FqP>(r.c1.l, a.c0.l, b.c1.l, a.c1.l, b.c0.l);
+    return r;
+#elif defined(__CUDA_ARCH__) && defined(P2B_FQ2_LAZY)
     // lazy reduction: three 512-bit products, two Montgomery reductions (336 instead of 408 wide multiply-adds)
     //   c0 = (a0 b0 - a1 b1 + q^2) / R      in (0, 2 q^2) < q 2^256
     //   c1 = ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) / R = (a0 b1 + a1 b0) / R   in [0, 2 q^2)

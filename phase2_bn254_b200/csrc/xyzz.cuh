@@ -31,7 +31,7 @@ template <class F> P2B_HD Xyzz<F> xyzz_dbl(const Xyzz<F> &p) {
     F xx = sqr(p.x), m = add(dbl(xx), xx);
     Xyzz<F> r;
     r.x = sub(sub(sqr(m), s), s);
-    r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+    r.y = mul_sub2(m, sub(s, r.x), w, p.y);
     r.zz = mul(v, p.zz); r.zzz = mul(w, p.zzz);
     return r;                                    // infinity (zz = 0) stays infinity
 }
@@ -84,7 +84,7 @@ template <class F> P2B_HD Xyzz<F> xyzz_add(const Xyzz<F> &p, const Xyzz<F> &q) {
     F pp = sqr(pp_), ppp = mul(pp_, pp), qq = mul(u1, pp);
     Xyzz<F> r;
     r.x = sub(sub(sub(sqr(rr), ppp), qq), qq);
-    r.y = sub(mul(rr, sub(qq, r.x)), mul(s1, ppp));
+    r.y = mul_sub2(rr, sub(qq, r.x), s1, ppp);
     r.zz = mul(mul(p.zz, q.zz), pp); r.zzz = mul(mul(p.zzz, q.zzz), ppp);
     bool p_inf = is_zero(p.zz), q_inf = is_zero(q.zz);
     if (!p_inf & !q_inf & is_zero(pp_) & is_zero(rr)) r = xyzz_dbl(p);
