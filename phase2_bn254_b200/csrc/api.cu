@@ -514,7 +514,7 @@ void p2b_destroy(p2b_ctx *h) { P2B_RANGE("p2b_destroy");
     if (c->stream) cudaStreamSynchronize(c->stream);
     io_destroy(c);
     DevBuf *bufs[] = {&c->jac, &c->prefix, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1], &c->scal,
-                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->msm_f, &c->fft_tw, &c->gtable, &c->gfft};
+                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->msm_f, &c->fft_tw_dir[0], &c->fft_tw_dir[1], &c->gtable, &c->gfft};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &sl : c->prof_slot)
         for (auto &e : sl.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }

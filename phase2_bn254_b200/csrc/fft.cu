@@ -280,7 +280,9 @@ static FftPlan fft_plan(uint32_t log_n) {
 }
 
 static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
-    if (c->fft_tw.p && c->fft_tw_log_n == log_n && c->fft_tw_inverse == inverse) return P2B_OK;
+    // one table set per direction: alternating fft / ifft calls (EvaluationDomain round trips, the prover's pattern) keep both
+    DevBuf &tw = c->fft_tw_dir[inverse ? 1 : 0];
+    if (tw.p && c->fft_tw_dir_log_n[inverse ? 1 : 0] == log_n) return P2B_OK;
     const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
     const size_t nent = ((size_t)1 << lb) + ((size_t)1 << hb) + 128;
     // [omega tables | coset tables | thi x n^-1 | direct tables of the passes whose omega_(Ns R) table has <= 2^FFT_DIRECT_LOG entries]
@@ -288,37 +290,36 @@ static int fft_tables(Ctx *c, uint32_t log_n, int inverse) {
     size_t ndirect = 0;
     for (uint32_t i = 1, lns = plan.r[0]; i < plan.npass; lns += plan.r[i], i++)
         if (lns + plan.r[i] <= FFT_DIRECT_LOG) ndirect += (size_t)1 << (lns + plan.r[i]);
-    int rc = dev_reserve(c, c->fft_tw, (2 * nent + ((size_t)1 << hb) + ndirect) * sizeof(Fr));
+    int rc = dev_reserve(c, tw, (2 * nent + ((size_t)1 << hb) + ndirect) * sizeof(Fr));
     if (rc) return rc;
     Fr root = host_root_of_unity(), omega = root, root256 = root;
     for (uint32_t i = log_n; i < 28; i++) omega = sqr(omega);
     for (uint32_t i = FFT_RMAX; i < 28; i++) root256 = sqr(root256);
     Fr g = host_fr_from_u64(7);
     if (inverse) { omega = inv(omega); root256 = inv(root256); g = inv(g); }
-    Fr *tlo = (Fr *)c->fft_tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
+    Fr *tlo = (Fr *)tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
     Fr *glo = twr + 128, *ghi = glo + ((size_t)1 << lb);
     const uint32_t threads = (uint32_t)nent;
     k_fft_tables<<<(threads + 127) / 128, 128, 0, c->stream>>>(tlo, thi, twr, omega, root256, lb, hb, 0);
     k_fft_tables<<<(threads + 127) / 128, 128, 0, c->stream>>>(glo, ghi, nullptr, g, g, lb, hb, 1);
     // inverse transform: the 1/n is folded into the high twiddle table the LAST pass uses (no separate multiplication)
     Fr ninv = inverse ? inv(host_fr_from_u64((uint64_t)1 << log_n)) : fp_one<FrP>();
-    k_fft_scale_table<<<(int)((((size_t)1 << hb) + 127) / 128), 128, 0, c->stream>>>((Fr *)c->fft_tw.p + 2 * nent, thi, (uint32_t)1 << hb, ninv);
+    k_fft_scale_table<<<(int)((((size_t)1 << hb) + 127) / 128), 128, 0, c->stream>>>((Fr *)tw.p + 2 * nent, thi, (uint32_t)1 << hb, ninv);
     c->launches += 3;
     {
-        Fr *dir = (Fr *)c->fft_tw.p + 2 * nent + ((size_t)1 << hb);
+        Fr *dir = (Fr *)tw.p + 2 * nent + ((size_t)1 << hb);
         for (uint32_t i = 1, lns = plan.r[0]; i < plan.npass; lns += plan.r[i], i++) {
             const uint32_t bits = lns + plan.r[i];
             if (bits > FFT_DIRECT_LOG) continue;
             const bool last = i + 1 == plan.npass;
             k_fft_direct_table<<<(int)((((size_t)1 << bits) + 127) / 128), 128, 0, c->stream>>>(
-                dir, tlo, last ? (const Fr *)((Fr *)c->fft_tw.p + 2 * nent) : (const Fr *)thi, lb, log_n - bits, 1u << bits);
+                dir, tlo, last ? (const Fr *)((Fr *)tw.p + 2 * nent) : (const Fr *)thi, lb, log_n - bits, 1u << bits);
             c->launches++;
             dir += (size_t)1 << bits;
         }
     }
     P2B_CUDA(c, cudaGetLastError());
-    c->fft_tw_log_n = log_n;
-    c->fft_tw_inverse = inverse;
+    c->fft_tw_dir_log_n[inverse ? 1 : 0] = log_n;
     return P2B_OK;
 }
 
@@ -342,11 +343,12 @@ static int fft_run(Ctx *c, void *d_data, void *d_tmp, uint32_t log_n, int invers
     if (log_n > 28) return ctx_fail(c, P2B_EARG, "fft: log_n must be <= 28 (Fr::S, domain.rs:64-78)");
     int rc = fft_tables(c, log_n, inverse);
     if (rc) return rc;
+    DevBuf &tw = c->fft_tw_dir[inverse ? 1 : 0];
     const size_t n = (size_t)1 << log_n;
     const uint32_t lb = (log_n + 1) / 2, hb = log_n - lb;
-    Fr *tlo = (Fr *)c->fft_tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
+    Fr *tlo = (Fr *)tw.p, *thi = tlo + ((size_t)1 << lb), *twr = thi + ((size_t)1 << hb);
     Fr *glo = twr + 128, *ghi = glo + ((size_t)1 << lb);
-    const Fr *thi_scaled = (const Fr *)c->fft_tw.p + 2 * (((size_t)1 << lb) + ((size_t)1 << hb) + 128);
+    const Fr *thi_scaled = (const Fr *)tw.p + 2 * (((size_t)1 << lb) + ((size_t)1 << hb) + 128);
     int sgrid = (int)((n + 255) / 256);
     if (sgrid > c->sm_count * 8) sgrid = c->sm_count * 8;
     if (coset && !inverse) {   // coset_fft: distribute_powers(g) then fft (domain.rs:191-195)

@@ -315,6 +315,55 @@ static __global__ void __launch_bounds__(256) k_msm_size_scatter(const uint32_t 
     }
 }
 
+// The same two steps with block-private histograms in shared memory: with uniform scalars nearly all buckets of a group have one
+// of ~100 sizes, so the global-atomic versions above serialise on a handful of counters (5 ms each per 2^26 MSM).  Here a block
+// counts its 4096 slots in shared memory (each thread keeps the rank its atomicAdd returned), reserves a range per non-empty
+// size class with ONE global atomicAdd, and writes its slots into those ranges.  nbins * 8 bytes of dynamic shared memory.
+static constexpr uint32_t SIZE_TILE = 4096;      // slots per block iteration: 256 threads x 16
+static __global__ void __launch_bounds__(256) k_msm_size_hist_smem(const uint32_t *offsets, uint32_t slot_cnt, uint32_t cap, uint32_t *size_hist,
+                                                                   uint32_t nbins) {
+    extern __shared__ uint32_t sm_bins[];
+    for (uint32_t b = threadIdx.x; b < nbins; b += 256) sm_bins[b] = 0;
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * SIZE_TILE; base < slot_cnt; base += gridDim.x * SIZE_TILE) {
+        for (uint32_t k = 0; k < 16; k++) {
+            const uint32_t i = base + k * 256 + threadIdx.x;
+            if (i < slot_cnt) {
+                const uint32_t sz = offsets[i + 1] - offsets[i];
+                atomicAdd(&sm_bins[sz < cap ? sz : cap], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += 256)
+        if (sm_bins[b]) atomicAdd(&size_hist[b], sm_bins[b]);
+}
+static __global__ void __launch_bounds__(256) k_msm_size_scatter_smem(const uint32_t *offsets, uint32_t slot_cnt, uint32_t cap, uint32_t *size_start,
+                                                                      uint32_t *perm, uint32_t nbins) {
+    extern __shared__ uint32_t sm_bins[];           // [0, nbins): counts, then the reserved base of each class
+    for (uint32_t base = blockIdx.x * SIZE_TILE; base < slot_cnt; base += gridDim.x * SIZE_TILE) {
+        for (uint32_t b = threadIdx.x; b < nbins; b += 256) sm_bins[b] = 0;
+        __syncthreads();
+        uint32_t bin[16], rank[16];
+        for (uint32_t k = 0; k < 16; k++) {
+            const uint32_t i = base + k * 256 + threadIdx.x;
+            bin[k] = 0xffffffffu;
+            if (i < slot_cnt) {
+                const uint32_t sz = offsets[i + 1] - offsets[i];
+                bin[k] = sz < cap ? sz : cap;
+                rank[k] = atomicAdd(&sm_bins[bin[k]], 1u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < nbins; b += 256)
+            if (sm_bins[b]) sm_bins[b] = atomicAdd(&size_start[b], sm_bins[b]);
+        __syncthreads();
+        for (uint32_t k = 0; k < 16; k++)
+            if (bin[k] != 0xffffffffu) perm[sm_bins[bin[k]] + rank[k]] = base + k * 256 + threadIdx.x;
+        __syncthreads();
+    }
+}
+
 // Skewed inputs (many equal digits) would put most terms of a window into one bucket and serialise them on one thread.
 // A bucket thread therefore takes at most `seg` entries; the rest is cut into items of `chunk` entries that whole blocks
 // reduce (k_msm_heavy) and a last kernel folds into the bucket (k_msm_heavy_combine).  Uniform scalars never overflow
@@ -980,9 +1029,18 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
         k_msm_scatter<<<grid, 256, 0, S>>>((const uint32_t *)j.d_scalars, n, g, cursor, sorted, w_lo, w_hi);
         {   // order the group's buckets by size (see k_msm_size_hist)
             const int sgrid = (int)((slot_cnt + 255) / 256) < c->sm_count * 8 ? (int)((slot_cnt + 255) / 256) : c->sm_count * 8;
-            k_msm_size_hist<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_hist);
-            k_msm_size_scan<<<1, 1024, 0, S>>>(size_hist, size_start, hv.seg + 1);
-            k_msm_size_scatter<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_start, perm + slot_lo);
+            const uint32_t nbins = hv.seg + 1;
+            if (nbins * 4 <= 40960) {                // block-private histograms in shared memory
+                int tgrid = (int)((slot_cnt + SIZE_TILE - 1) / SIZE_TILE);
+                if (tgrid > c->sm_count * 4) tgrid = c->sm_count * 4;
+                k_msm_size_hist_smem<<<tgrid, 256, nbins * 4, S>>>(offs, slot_cnt, hv.seg, size_hist, nbins);
+                k_msm_size_scan<<<1, 1024, 0, S>>>(size_hist, size_start, nbins);
+                k_msm_size_scatter_smem<<<tgrid, 256, nbins * 4, S>>>(offs, slot_cnt, hv.seg, size_start, perm + slot_lo, nbins);
+            } else {
+                k_msm_size_hist<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_hist);
+                k_msm_size_scan<<<1, 1024, 0, S>>>(size_hist, size_start, nbins);
+                k_msm_size_scatter<<<sgrid, 256, 0, S>>>(offs, slot_cnt, hv.seg, size_start, perm + slot_lo);
+            }
         }
         if (gi + 1 == ngroups) prof_end(c, P2B_PROF_MSM_SORT, (int)(8 * ngroups), S);
         if (S != C) {

@@ -36,7 +36,7 @@ struct Ctx {
     unsigned long long *d_err = nullptr;   // device error word
     unsigned long long *h_err = nullptr;   // pinned mirror
     // growable device scratch
-    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, msm_f, fft_tw, gtable, gfft;
+    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, msm_f, fft_tw_dir[2], gtable, gfft;
     // pinned staging rings + copy threads for pageable caller buffers (hostio.cu), created on first use
     HostIO *io = nullptr;
     cudaEvent_t ev[8] = {};
@@ -47,9 +47,8 @@ struct Ctx {
         size_t used = 0;
         uint64_t kernels = 0;
     } prof_slot[P2B_PROF_SLOTS];
-    // cached FFT twiddle state
-    uint32_t fft_tw_log_n = 0;
-    int fft_tw_inverse = -1;
+    // cached FFT twiddle tables, one set per direction (fft_tw_dir[0] forward, [1] inverse)
+    uint32_t fft_tw_dir_log_n[2] = {0xffffffffu, 0xffffffffu};
 };
 
 int ctx_fail(Ctx *c, int code, const std::string &msg);
