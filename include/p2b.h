@@ -203,6 +203,13 @@ int p2b_random_scalars(p2b_ctx *ctx, const uint8_t seed[32], uint64_t first_inde
 int p2b_g1_sum_points(p2b_ctx *ctx, const uint8_t *points, size_t count, uint8_t out[64]);
 int p2b_g2_sum_points(p2b_ctx *ctx, const uint8_t *points, size_t count, uint8_t out[128]);
 
+/* ---- self-test of the device multipliers (used by tests/test_gpu_field_selftest.py) ----
+ * out[i] = op(a[i], b[i], c[i], d[i]) on RAW 8 x u32 little-endian limbs (no conversions: Montgomery form is the caller's business).
+ * op: 0 a*b/R, 1 a^2/R (dedicated squaring), 2 (a*b + c*d)/R (the fused two-product multiplication), 3 reduce(wide product of a, b),
+ * 4 a + b, 5 a - b (mod p); field: 0 Fq, 1 Fr.  Operands must be < p. */
+int p2b_selftest_field(p2b_ctx *ctx, int field, int op, const uint8_t *a, const uint8_t *b, const uint8_t *c, const uint8_t *d,
+                       size_t n, uint8_t *out);
+
 /* ---- Fr radix-2 FFT ---- */
 /* In-place, natural order in and out, 2^log_n scalars of 32 BE bytes; inverse => ifft (x m^-1);
  * coset => coset_fft / icoset_fft with the multiplicative generator 7. */

@@ -32,7 +32,7 @@ SYMBOLS = [
     "p2b_pairing_check", "p2b_same_ratio", "p2b_hash_to_g2", "p2b_rng_seed", "p2b_rng_u32", "p2b_rng_fr", "p2b_rng_g1",
     "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants", "p2b_io_stats",
     "p2b_g1_msm_pair", "p2b_g2_msm_pair", "p2b_g1_power_pairs", "p2b_g2_power_pairs", "p2b_random_scalars", "p2b_phase2_contribute_sharded",
-    "p2b_g1_group_fft_scaled", "p2b_g2_group_fft_scaled", "p2b_g1_gfft_stage", "p2b_g2_gfft_stage", "p2b_fr_root_of_unity",
+    "p2b_g1_group_fft_scaled", "p2b_g2_group_fft_scaled", "p2b_g1_gfft_stage", "p2b_g2_gfft_stage", "p2b_fr_root_of_unity", "p2b_selftest_field",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -102,6 +102,7 @@ def load():
         getattr(lib, "p2b_%s_group_fft_scaled" % g).argtypes = [vp, u8p, u8p, u32, i32, i32, i32, i32, u32]
         getattr(lib, "p2b_%s_gfft_stage" % g).argtypes = [vp, u8p, u8p, u32, u8p, u64, i32, i32, i32, u8p, u8p]
     lib.p2b_fr_root_of_unity.argtypes = [u32, i32, u8p]
+    lib.p2b_selftest_field.argtypes = [vp, i32, i32, u8p, u8p, u8p, u8p, sz, u8p]
     lib.p2b_pot_radix_file_size.argtypes = [u32]
     lib.p2b_pot_radix_file_size.restype = u64
     lib.p2b_pot_prepare_phase2.argtypes = [vp, u8p, u64, u32, i32, i32, u32, u8p, u64, i32]
@@ -437,6 +438,16 @@ class Context:
         """The coefficients the device generates for (seed, scalar_bits): n x 32 bytes big-endian."""
         out = np.empty(max(1, 32 * n), dtype=np.uint8)
         self._check(self.lib.p2b_random_scalars(self.h, _ptr(_fixed(seed, 32, "seed")), first, n, scalar_bits, _ptr(out)))
+        return out[: 32 * n]
+
+    def selftest_field(self, field, op, a, b, c=None, d=None):
+        """Element-wise device field operation on raw little-endian limbs (see p2b_selftest_field); arrays of n x 32 bytes."""
+        a, b = _host(a), _host(b)
+        c = _host(c) if c is not None else a
+        d = _host(d) if d is not None else b
+        n = a.size // 32
+        out = np.empty(max(1, a.size), dtype=np.uint8)
+        self._check(self.lib.p2b_selftest_field(self.h, field, op, _ptr(a), _ptr(b), _ptr(c), _ptr(d), n, _ptr(out)))
         return out[: 32 * n]
 
     def sparse_mul(self, group, bases, row_offsets, cols, coeffs):
