@@ -45,7 +45,15 @@ static int random_scalars_dev(Ctx *c, uint32_t *d_scalars, size_t n, uint64_t fi
 // Host buffers larger than STREAM_MIN terms are streamed: chunks of up to STREAM_CHUNK terms are copied on the H2D stream into
 // a double-buffered staging area while the previous chunk is sorted and accumulated into the SAME buckets; the bucket
 // reduction runs once at the end.  The sum is unchanged (bucket contents are sums of the same terms).
-static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 25;
+// Chunk size: 2^22 terms.  Measured at 2^26 terms (tools/e2e_probe.py): maximum chunk 2^25 189.5 ms, 2^24 183.5, 2^23 181.1, 2^22 177.1,
+// 2^21 178.1, 2^20 186.5, 2^19 222 -- small chunks keep the points a chunk's accumulation gathers (2^22 x 64 B = 268 MB) largely in
+// the 126 MB L2 across the 14 windows, which outweighs the per-chunk sort and the reload of the bucket accumulators; the streamed
+// MSM then runs as fast as the device-resident one, and device-resident inputs are tiled the same way (P2B_MSM_TILE).
+static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 22;
+static size_t msm_tile() {               // P2B_MSM_TILE=<terms> (0 = no tiling of device-resident inputs): tuning / test hook
+    const char *e = getenv("P2B_MSM_TILE");
+    return e ? (size_t)atol(e) : MSM_STREAM_CHUNK;
+}
 // growth of the chunk sizes, in eighths (P2B_MSM_STREAM_GROWTH, tuning): a chunk's copy (1.75 ns per G1 term over PCIe 5) hides
 // behind the work on the terms already there (2.8 ns per term) only while the cumulative size grows by <= 1.6x per chunk;
 // plain doubling makes the GPU wait for the copy of every chunk from the fourth on
@@ -76,7 +84,10 @@ static int msm_call(Ctx *c, const MsmCall &a) {
     const size_t extra = a.pair == MSM_PAIR_SHIFTED ? 1 : 0;
     const size_t ov = msm_stream_chunk();
     const bool streamed = !a.dev && a.n > (ov ? ov : MSM_STREAM_MIN);
-    const size_t chunk = streamed ? (ov ? ov : MSM_STREAM_CHUNK) : (a.n ? a.n : 1);
+    // device-resident input: same chunks, no copies (above 2^23 terms; above the tile size when the hook overrides it)
+    const bool tiled = a.dev && msm_tile() && a.n > (getenv("P2B_MSM_TILE") ? msm_tile() : MSM_STREAM_MIN);
+    const bool chunked = streamed || tiled;
+    const size_t chunk = streamed ? (ov ? ov : MSM_STREAM_CHUNK) : tiled ? msm_tile() : (a.n ? a.n : 1);
     if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
     uint32_t *d_out = (uint32_t *)c->misc.p;
     // staging per buffer: points A (chunk + 1), points B (chunk), scalars (chunk)
@@ -97,7 +108,9 @@ static int msm_call(Ctx *c, const MsmCall &a) {
     // last chunk, which nothing overlaps -- so the plan then ends with small chunks (1/4, 1/8, 1/8 of the maximum) and uses a
     // smaller maximum.  The link speed is the one measured on this context's previous streamed call (c->h2d_gbps).
     std::vector<size_t> plan;
-    if (!streamed) plan.push_back(a.n);
+    if (tiled) {
+        for (size_t rem = a.n; rem;) { const size_t m = rem < chunk ? rem : chunk; plan.push_back(m); rem -= m; }
+    } else if (!streamed) plan.push_back(a.n);
     else {
         const double ns_copy = c->h2d_gbps > 0 ? (double)(psz * (a.pair == MSM_PAIR_SEPARATE ? 2 : 1) + (a.scalars ? 32 : 0)) / c->h2d_gbps : 0;
         const double ns_compute = (a.g2 ? 10.0 : 2.8) * (pair ? 2.0 : 1.0);      // per term, measured (bench.py, one B200)
@@ -140,7 +153,9 @@ static int msm_call(Ctx *c, const MsmCall &a) {
         const size_t m = plan[ci];
         const void *d_pts = nullptr, *d_pts_b = nullptr, *d_sc = nullptr;
         if (a.dev) {
-            d_pts = a.points; d_pts_b = a.points_b; d_sc = a.scalars;
+            d_pts = a.points + off * isz;
+            d_pts_b = a.points_b ? a.points_b + off * isz : nullptr;
+            d_sc = a.scalars ? a.scalars + off * 32 : nullptr;
         } else {
             if (streamed) P2B_CUDA(c, cudaStreamWaitEvent(CP, ci >= 2 ? ev_done[b] : c->ev[6], 0));
             if (ci == probe_ci) P2B_CUDA(c, cudaEventRecord(c->h2d_ev[0], CP));
@@ -170,7 +185,7 @@ static int msm_call(Ctx *c, const MsmCall &a) {
             P2B_CUDA(c, cudaStreamWaitEvent(c->stream, ev_in[b], 0));
         }
         MsmJob j;
-        j.n = m; j.d_scalars = d_sc; j.d_out_wire = d_out; j.geom_n = chunk; j.err_base = off; j.total_n = streamed ? a.n : 0;
+        j.n = m; j.d_scalars = d_sc; j.d_out_wire = d_out; j.geom_n = chunk; j.err_base = off; j.total_n = chunked ? a.n : 0;
         j.phase = (ci == 0 ? MSM_FIRST : 0) | (off + m == a.n ? MSM_LAST : 0);
         j.pair = a.pair; j.scalar_bits = a.scalar_bits;
         if (compressed) {     // decompress (square root per point) into raw Montgomery form; the MSM's prepare kernel then only copies

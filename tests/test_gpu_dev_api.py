@@ -63,3 +63,16 @@ def test_msm_and_fft_dev_match_host(ctx, oracle):
     ctx.fr_fft_dev(d_x.data_ptr(), 12, False, False)
     ctx.sync()
     assert ctx.launch_count > before
+
+
+@pytest.mark.parametrize("group", [0, 1])
+def test_msm_dev_tiled(ctx, oracle, group, monkeypatch):
+    """Device-resident inputs above the tile size are accumulated tile by tile into the same buckets (L2 locality of the
+    gathers); the hook lowers the tile size so that the path runs at test sizes, including a ragged last tile."""
+    n = 2500
+    pts, sc = random_points(oracle, group, n, seed=811 + group), random_scalars(n, seed=812)
+    d_p, d_s = dev(pts), dev(sc)
+    exp = oracle.msm(group, pts, sc, threads=8)
+    for tile in ("700", "1024", "2499", "0"):
+        monkeypatch.setenv("P2B_MSM_TILE", tile)
+        assert ctx.msm_dev(group, d_p.data_ptr(), d_s.data_ptr(), n) == exp, tile
