@@ -49,7 +49,10 @@ static int random_scalars_dev(Ctx *c, uint32_t *d_scalars, size_t n, uint64_t fi
 // 2^21 178.1, 2^20 186.5, 2^19 222 -- small chunks keep the points a chunk's accumulation gathers (2^22 x 64 B = 268 MB) largely in
 // the 126 MB L2 across the 14 windows, which outweighs the per-chunk sort and the reload of the bucket accumulators; the streamed
 // MSM then runs as fast as the device-resident one, and device-resident inputs are tiled the same way (P2B_MSM_TILE).
-static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 22;
+// G2 does not gain from it (its gathers are whole 128-byte lines and a term costs 3.5x the arithmetic; measured at 2^25: untiled
+// 301 ms, tiles of 2^20 / 2^21 / 2^22 terms 311 / 311 / 308 ms): device-resident G2 inputs are not tiled, host buffers stream in
+// 2^24-term chunks.
+static constexpr size_t MSM_STREAM_MIN = (size_t)1 << 23, MSM_STREAM_CHUNK = (size_t)1 << 22, MSM_STREAM_CHUNK_G2 = (size_t)1 << 24;
 static size_t msm_tile() {               // P2B_MSM_TILE=<terms> (0 = no tiling of device-resident inputs): tuning / test hook
     const char *e = getenv("P2B_MSM_TILE");
     return e ? (size_t)atol(e) : MSM_STREAM_CHUNK;
@@ -85,9 +88,10 @@ static int msm_call(Ctx *c, const MsmCall &a) {
     const size_t ov = msm_stream_chunk();
     const bool streamed = !a.dev && a.n > (ov ? ov : MSM_STREAM_MIN);
     // device-resident input: same chunks, no copies (above 2^23 terms; above the tile size when the hook overrides it)
-    const bool tiled = a.dev && msm_tile() && a.n > (getenv("P2B_MSM_TILE") ? msm_tile() : MSM_STREAM_MIN);
+    const bool tile_hook = getenv("P2B_MSM_TILE") != nullptr;
+    const bool tiled = a.dev && msm_tile() && (tile_hook || !a.g2) && a.n > (tile_hook ? msm_tile() : MSM_STREAM_MIN);
     const bool chunked = streamed || tiled;
-    const size_t chunk = streamed ? (ov ? ov : MSM_STREAM_CHUNK) : tiled ? msm_tile() : (a.n ? a.n : 1);
+    const size_t chunk = streamed ? (ov ? ov : (a.g2 ? MSM_STREAM_CHUNK_G2 : MSM_STREAM_CHUNK)) : tiled ? msm_tile() : (a.n ? a.n : 1);
     if ((rc = dev_reserve(c, c->misc, 4096))) return rc;
     uint32_t *d_out = (uint32_t *)c->misc.p;
     // staging per buffer: points A (chunk + 1), points B (chunk), scalars (chunk)
