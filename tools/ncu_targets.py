@@ -29,4 +29,10 @@ if what in ("all", "msm"):
     p = bench.make_points(torch, np, ctx, 0, n, 1, dev)
     s = bench.make_scalars(torch, n, 2, dev)
     print(ctx.msm_dev(0, p.data_ptr(), s.data_ptr(), n)[:8].hex())
+if what == "msm_g2":
+    lg = int(os.environ.get("MSM_LOG", "22"))
+    n = 1 << lg
+    p = bench.make_points(torch, np, ctx, 1, n, 1, dev)
+    s = bench.make_scalars(torch, n, 2, dev)
+    print(ctx.msm_dev(1, p.data_ptr(), s.data_ptr(), n)[:8].hex())
 print("done", what)
