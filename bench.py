@@ -795,7 +795,13 @@ def extras(args, torch, np, ctx, stream, device, lib, pts, sc):
     o2 = torch.empty(m2 * 128, dtype=torch.uint8, device=device)
     ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), 1024, k); ctx.sync()
     t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), m2, k), ctx.sync()), 2)
-    out["g2_batch_exp_2^20"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2)}
+    out["g2_batch_exp_2^20"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2), "probe_verdict": ctx.g2_probe_stats()[1],
+                                "note": "default: batch subgroup probe on the device (8 random window sums, [r]W = O), then the "
+                                        "endomorphism split; verdict 0 = proven"}
+    ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), 1024, k, flags=lib.G2_EXACT); ctx.sync()
+    t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), m2, k, flags=lib.G2_EXACT), ctx.sync()), 2)
+    out["g2_batch_exp_2^20_exact_flag"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2),
+                                           "note": "P2B_G2_EXACT: no probe, no split (the path a batch with a point outside the subgroup takes)"}
     ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), 1024, k, flags=lib.G2_SUBGROUP); ctx.sync()
     t, _ = timed(torch, stream, lambda: (ctx.batch_mul_dev(1, p2.data_ptr(), o2.data_ptr(), m2, k, flags=lib.G2_SUBGROUP), ctx.sync()), 2)
     out["g2_batch_exp_2^20_subgroup_flag"] = {"ms": round(t, 3), "Mmul_per_s": round(m2 / t / 1e3, 2),

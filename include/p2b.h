@@ -60,10 +60,17 @@ enum { P2B_ENC_UNCOMPRESSED = 0, P2B_ENC_COMPRESSED = 1, P2B_ENC_RAW_MONT_LE = 2
 enum { /* flags */
     P2B_CHECK_INPUT = 1,     /* CheckForCorrectness::Yes: is_on_curve on every decoded point */
     P2B_REJECT_INFINITY = 2, /* infinity in the input or the output is an error (phase-1 semantics) */
-    P2B_G2_SUBGROUP = 4      /* the caller vouches that every G2 input lies in the order-r subgroup (true for any point
+    P2B_G2_SUBGROUP = 4,     /* the caller vouches that every G2 input lies in the order-r subgroup (true for any point
                                 produced by scalar multiplication of the generator): enables the endomorphism-split G2
                                 path (~1.4x faster).  Without it G2 results are exact for EVERY on-curve point, like the
                                 reference, which decodes G2 without a subgroup check (pairing/src/bn256/ec.rs:1145-1213). */
+    P2B_G2_EXACT = 8         /* never use the endomorphism split for G2.  Without P2B_G2_SUBGROUP and P2B_G2_EXACT a G2 batch of
+                                >= 2^17 points is first PROVEN to lie in the order-r subgroup by the library itself (random
+                                linear combinations of the whole batch, 8 independent 14..16-bit window sums W_j = sum rho_ij P_i
+                                tested for [r] W_j = O; every on-curve point outside the subgroup is caught with probability
+                                >= 1 - 2^-104 over the library's CSPRNG coefficients, an off-curve point always) and then takes
+                                the split path; a batch that fails the test takes the exact path.  Results are the exact [k]P
+                                either way. */
 };
 
 /* ---- context ---- */
@@ -77,6 +84,9 @@ void *p2b_stream(p2b_ctx *ctx);
 /* number of kernels this ctx has launched so far */
 uint64_t p2b_launch_count(p2b_ctx *ctx);
 const char *p2b_version(void);
+/* G2 subgroup probe (see P2B_G2_EXACT): number of batches probed so far by this ctx, and the verdict of the last one
+ * (0 = proven in the subgroup, split path taken; 1 = exact path taken; -1 = no probe yet).  Waits for the ctx's stream. */
+int p2b_g2_probe_stats(p2b_ctx *ctx, uint64_t *probes, int *last_verdict);
 /* Profiling: when enabled, the ctx brackets its dominant kernels with CUDA events on p2b_stream(ctx) (the stream they
  * are launched on).  p2b_profile_read waits for the stream and returns the summed device time and the number of kernel
  * launches recorded in `slot` since p2b_profile_enable(ctx, 1) was last called (which also resets the counters). */

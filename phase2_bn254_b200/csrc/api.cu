@@ -514,7 +514,7 @@ void p2b_destroy(p2b_ctx *h) { P2B_RANGE("p2b_destroy");
     if (c->stream) cudaStreamSynchronize(c->stream);
     io_destroy(c);
     DevBuf *bufs[] = {&c->jac, &c->prefix, &c->stage_in[0], &c->stage_in[1], &c->stage_out[0], &c->stage_out[1], &c->scal,
-                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->msm_f, &c->fft_tw_dir[0], &c->fft_tw_dir[1], &c->gtable, &c->gfft};
+                      &c->tables, &c->misc, &c->msm_a, &c->msm_b, &c->msm_c, &c->msm_d, &c->msm_e, &c->msm_f, &c->fft_tw_dir[0], &c->fft_tw_dir[1], &c->gtable, &c->gfft, &c->probe};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &sl : c->prof_slot)
         for (auto &e : sl.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -538,6 +538,22 @@ void p2b_error_detail(p2b_ctx *h, uint64_t *index, int *sub) {
 }
 void *p2b_stream(p2b_ctx *h) { return h ? (void *)h->c.stream : nullptr; }
 uint64_t p2b_launch_count(p2b_ctx *h) { return h ? h->c.launches : 0; }
+int p2b_g2_probe_stats(p2b_ctx *h, uint64_t *probes, int *last_verdict) {
+    if (!h) return P2B_EARG;
+    Ctx *c = &h->c;
+    if (probes) *probes = c->probes;
+    if (last_verdict) {
+        *last_verdict = -1;
+        if (c->probes && c->probe.p) {
+            uint32_t v = 0;
+            P2B_CUDA(c, cudaSetDevice(c->device));
+            P2B_CUDA(c, cudaStreamSynchronize(c->stream));
+            P2B_CUDA(c, cudaMemcpy(&v, c->probe.p, 4, cudaMemcpyDeviceToHost));
+            *last_verdict = v ? 1 : 0;
+        }
+    }
+    return P2B_OK;
+}
 
 void p2b_io_stats(p2b_ctx *h, uint64_t *staged_in, uint64_t *staged_out) {
     if (h) io_stats(&h->c, staged_in, staged_out);

@@ -181,6 +181,8 @@ struct BatchMulParams {
     uint64_t err_base;
     uint4 *gtable;             // G2: per-thread odd-multiples tables in global memory (grid * block columns)
     UniformDigits uni;         // UNIFORM kernels (mode 1): width-5 NAF of the GLV halves of the one scalar
+    const uint32_t *route;     // G2 subgroup probe (msm_g2.cu): the launch only runs when *route == route_want (nullptr: always)
+    uint32_t route_want;
 };
 
 // table policy: G1 keeps its 512 B / thread table in shared memory; G2 (1 KB / thread) keeps it in L2 so that two
@@ -214,6 +216,8 @@ template <class F, int BLOCK, bool GLV, bool UNIFORM = false> __global__ void __
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     constexpr bool IS_G1 = FieldTraits<F>::WORDS == 8;
     const int tid = threadIdx.x;
+    // probed G2 batches queue BOTH the split and the exact kernel; the device-side verdict picks the one that runs
+    if (p.route && (__ldg(p.route) != 0u) != (p.route_want != 0u)) return;
     const auto tbl = TablePolicy<F, BLOCK>::make(smem, p);
     const size_t ntiles = (p.n + BLOCK - 1) / BLOCK;
     // staging area behind the table: 2 x point tile, 2 x scalar tile, 2 mbarriers
@@ -357,8 +361,12 @@ template <class F> __global__ void __launch_bounds__(128) k_normalize(NormalizeP
 static constexpr int G1_BLOCK = P2B_G1_BLOCK;
 static constexpr int G2_BLOCK = 128;
 
+// stages: which parts of the pipeline this call queues (a probed G2 batch is PROLOGUE | KERNEL with the split kernel, then
+// KERNEL | NORMALIZE with the exact one; the prologue's products -- decompressed points in c->misc, tau tables -- are reused)
+enum { BM_PROLOGUE = 1, BM_KERNEL = 2, BM_NORMALIZE = 4, BM_ALL = 7 };
 template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(Ctx *c, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc,
-                                                       int in_enc, int out_enc, int flags, uint64_t err_base) {
+                                                       int in_enc, int out_enc, int flags, uint64_t err_base, int stages = BM_ALL,
+                                                       const uint32_t *route = nullptr, uint32_t route_want = 0) {
     constexpr int W = FieldTraits<F>::WORDS;
     constexpr bool IS_G2 = W == 16;
     const size_t elem = (size_t)W * 4;
@@ -379,11 +387,13 @@ template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(C
     int kin_enc = in_enc;
     if (in_enc == P2B_ENC_COMPRESSED) {
         if ((rc = dev_reserve(c, c->misc, n * 2 * elem))) return rc;
-        DecompressParams dp{(const uint32_t *)d_in, (uint32_t *)c->misc.p, n, c->d_err, err_base};
-        int blocks = (int)((n + 127) / 128);
-        if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
-        k_decompress<F><<<blocks, 128, 0, c->stream>>>(dp);
-        c->launches++;
+        if (stages & BM_PROLOGUE) {
+            DecompressParams dp{(const uint32_t *)d_in, (uint32_t *)c->misc.p, n, c->d_err, err_base};
+            int blocks = (int)((n + 127) / 128);
+            if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+            k_decompress<F><<<blocks, 128, 0, c->stream>>>(dp);
+            c->launches++;
+        }
         in_words = (const uint32_t *)c->misc.p;
         kin_enc = ENC_RAW_MONT_LE;
     }
@@ -391,6 +401,7 @@ template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(C
     memset(&bp, 0, sizeof(bp));
     bp.in = in_words; bp.jx = jx; bp.jy = jy; bp.jz = jz; bp.n = n; bp.in_enc = kin_enc; bp.flags = flags;
     bp.sc_mode = sc.mode; bp.err = c->d_err; bp.err_base = err_base;
+    bp.route = route; bp.route_want = route_want;
     if (sc.mode == 0) bp.scalars = (const uint32_t *)sc.d_scalars;
     else if (sc.mode == 1) {
         memcpy(bp.k, sc.k, 32);
@@ -398,12 +409,14 @@ template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(C
     }
     else {
         if ((rc = dev_reserve(c, c->tables, 4096 * sizeof(Fr) + 64))) return rc;
-        uint32_t *d_tc = (uint32_t *)((char *)c->tables.p + 4096 * sizeof(Fr));
-        uint32_t tc[16];
-        memcpy(tc, sc.tau, 32); memcpy(tc + 8, sc.coeff, 32);
-        P2B_CUDA(c, cudaMemcpyAsync(d_tc, tc, 64, cudaMemcpyHostToDevice, c->stream));
-        k_pow_tables<<<4096 / 128, 128, 0, c->stream>>>((Fr *)c->tables.p, d_tc, d_tc + 8);
-        c->launches++;
+        if (stages & BM_PROLOGUE) {
+            uint32_t *d_tc = (uint32_t *)((char *)c->tables.p + 4096 * sizeof(Fr));
+            uint32_t tc[16];
+            memcpy(tc, sc.tau, 32); memcpy(tc + 8, sc.coeff, 32);
+            P2B_CUDA(c, cudaMemcpyAsync(d_tc, tc, 64, cudaMemcpyHostToDevice, c->stream));
+            k_pow_tables<<<4096 / 128, 128, 0, c->stream>>>((Fr *)c->tables.p, d_tc, d_tc + 8);
+            c->launches++;
+        }
         bp.tables = (const Fr *)c->tables.p;
         bp.start = sc.start;
     }
@@ -425,11 +438,13 @@ template <class F, int BLOCK, bool GLV, bool UNIFORM = false> int launch_typed(C
         if ((rc = dev_reserve(c, c->gtable, max_grid * BLOCK * 8 * 2 * W * 4))) return rc;
         bp.gtable = (uint4 *)c->gtable.p;
     }
-    if (grid > 0) {
+    if (grid > 0 && (stages & BM_KERNEL)) {
         prof_begin(c, P2B_PROF_BATCH_MUL);
         k_batch_mul<F, BLOCK, GLV, UNIFORM><<<grid, BLOCK, smem, c->stream>>>(bp);
         prof_end(c, P2B_PROF_BATCH_MUL, 1);
         c->launches++;
+    }
+    if (grid > 0 && (stages & BM_NORMALIZE)) {
         // ~32 points per thread in the normalisation pass, at least one full wave of 128-thread blocks
         size_t threads = (n + 31) / 32;
         if (threads < (size_t)c->sm_count * 128) threads = n < (size_t)c->sm_count * 128 ? n : (size_t)c->sm_count * 128;

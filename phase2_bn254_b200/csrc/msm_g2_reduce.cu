@@ -10,4 +10,7 @@ void msm_launch_reduce_g2(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uin
 void msm_launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out) {
     k_sum_points<Fq2><<<1, 32, 0, c->stream>>>(d_in, count, d_out, c->d_err);
 }
+void msm_launch_probe_order_g2(Ctx *c, const uint32_t *wsum, uint32_t nwin, uint32_t *route) {
+    k_msm_probe_order<Fq2><<<nwin, 32, 0, c->stream>>>(wsum, nwin, route);
+}
 }  // namespace p2b

@@ -114,8 +114,9 @@ static __device__ __forceinline__ void report_err(unsigned long long *err, uint6
 }
 
 // ------------------------------------------------------------------------------------------------- kernels
+// check bit 2 (subgroup probe): a finite point that is not on the curve raises *route (no error: such a batch takes the exact path)
 template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const uint32_t *wire, uint32_t *aff, size_t n, unsigned long long *err, uint64_t err_base,
-                                                                        int in_enc, int check) {
+                                                                        int in_enc, int check, uint32_t *route = nullptr) {
     constexpr int WU = Wire<F>::WORDS_UNCOMPRESSED;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t w[WU];
@@ -125,6 +126,7 @@ template <class F> __global__ void __launch_bounds__(256) k_msm_prepare(const ui
         int rc = point_decode<F>(a, inf, w, in_enc, (check & 1) != 0);     // in_enc: uncompressed wire, or RAW (already decoded)
         if (rc) { report_err(err, err_base + i, P2B_EDECODE, rc); inf = true; }
         else if (inf && (check & 2)) report_err(err, err_base + i, P2B_EINFINITY_IN, 0);
+        if ((check & 4) && !rc && !inf && !on_curve(a)) atomicOr(route, 1u);
         uint32_t o[WU];
         point_encode<F>(o, a, inf, ENC_RAW_MONT_LE);   // infinity = all-zero: skipped by the accumulator
         stw<WU>(aff + i * WU, o);
@@ -831,6 +833,21 @@ template <class F> __global__ void __launch_bounds__(32) k_msm_final(const uint3
     for (int j = 0; j < Wire<F>::WORDS_UNCOMPRESSED; j++) out_wire[j] = o[j];
 }
 
+// Subgroup probe: one warp per window sum W_w (XYZZ, any point of E'(Fq2)): [r] W_w by MSB-first double-and-add with the
+// lane-parallel complete formulas above; *route is raised unless the result is the point at infinity, i.e. unless W_w lies in
+// the order-r subgroup (#E'(Fq2) = r h with gcd(r, h) = 1, so E'[r] is exactly that subgroup).
+template <class F> __global__ void __launch_bounds__(32) k_msm_probe_order(const uint32_t *wsum, uint32_t nwin, uint32_t *route) {
+    if (blockIdx.x >= nwin) return;
+    const Xyzz<F> w = load_xyzz<F>(wsum, blockIdx.x);
+    Xyzz<F> acc = w;                                                   // bit 253 of r is its top bit
+#pragma unroll 1
+    for (int i = 252; i >= 0; i--) {
+        acc = xdbl_lanes(acc);
+        if ((FrP::p(i >> 5) >> (i & 31)) & 1u) acc = xadd_lanes(acc, w);      // warp-uniform
+    }
+    if (threadIdx.x == 0 && !is_zero(acc.zz)) atomicOr(route, 1u);
+}
+
 // sum of `count` affine wire points (multi-GPU combination of per-rank results)
 template <class F> __global__ void k_sum_points(const uint32_t *wire, uint32_t count, uint32_t *out_wire, unsigned long long *err) {
     if (threadIdx.x || blockIdx.x) return;
@@ -869,7 +886,7 @@ template <class F> void msm_launch_reduce_impl(Ctx *c, const uint32_t *buckets, 
     uint32_t *rows = wsum + (size_t)g.nwin * 4 * FieldTraits<F>::WORDS, *cnt = rows + (size_t)g.nwin * 96 * 4 * FieldTraits<F>::WORDS;
     cudaMemsetAsync(cnt, 0, (size_t)g.nwin * 4, c->stream);
     k_msm_reduce2<F><<<g.nwin * RED2_SPLIT, 256, 0, c->stream>>>(s1, s2, g, wsum, rows, cnt);
-    k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
+    if (d_out_wire) k_msm_final<F><<<1, 32, 0, c->stream>>>(wsum, g, d_out_wire);
 }
 void msm_launch_heavy_g1(Ctx *c, const uint32_t *aff, const uint32_t *sorted, uint32_t *buckets, const MsmHeavy &hv);
 void msm_launch_heavy_g2(Ctx *c, const uint32_t *aff, const uint32_t *sorted, uint32_t *buckets, const MsmHeavy &hv);
@@ -877,6 +894,7 @@ void msm_launch_reduce_g1(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uin
 void msm_launch_reduce_g2(Ctx *c, const uint32_t *buckets, const MsmGeom &g, uint32_t *s1, uint32_t *s2, uint32_t *wsum, uint32_t *d_out_wire, size_t nred);
 void msm_launch_sum_points_g1(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
 void msm_launch_sum_points_g2(Ctx *c, const uint32_t *d_in, uint32_t count, uint32_t *d_out);
+void msm_launch_probe_order_g2(Ctx *c, const uint32_t *wsum, uint32_t nwin, uint32_t *route);
 
 // Window geometry.  The 255 bits (r < 2^254 plus one bit of head-room for the signed-digit carry) are split into nwin
 // windows whose widths differ by at most one bit -- a short top window would put n / 2^bits terms into each of a few
@@ -931,6 +949,7 @@ struct MsmJob {
     int in_enc = ENC_UNCOMPRESSED;      // ENC_UNCOMPRESSED (wire) or ENC_RAW_MONT_LE (decoded by an earlier kernel)
     int check = 0;                      // bit 0: is_on_curve on every point (CheckForCorrectness::Yes); bit 1: infinity is an error
     uint32_t scalar_bits = 0;           // the caller guarantees scalars < 2^scalar_bits (0: any canonical scalar)
+    uint32_t *d_route = nullptr;        // check bit 2: device word raised when a point is off the curve (subgroup probe)
 };
 template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
     constexpr int W = FieldTraits<F>::WORDS, WU = Wire<F>::WORDS_UNCOMPRESSED;
@@ -1000,7 +1019,7 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
     P2B_CUDA(c, cudaMemsetAsync(size_hist, 0, ((size_t)hv.seg + 2) * 4, S));
     // the point decode is only needed by the accumulation: it runs on the compute stream, next to the first group's sort
     const size_t np_a = n + (j.pair == MSM_PAIR_SHIFTED ? 1 : 0);
-    k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)j.d_points, aff, np_a, c->d_err, j.err_base, j.in_enc, j.check);
+    k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)j.d_points, aff, np_a, c->d_err, j.err_base, j.in_enc, j.check, j.d_route);
     c->launches++;
     if (j.pair == MSM_PAIR_SEPARATE) {
         k_msm_prepare<F><<<grid, 256, 0, C>>>((const uint32_t *)j.d_points_b, aff_b, n, c->d_err, j.err_base, j.in_enc, j.check);
@@ -1094,12 +1113,14 @@ template <class F> int msm_typed(Ctx *c, const MsmJob &j) {
     prof_begin(c, P2B_PROF_MSM_REDUCE);
     for (size_t set = 0; set < nsets; set++) {
         const uint32_t *bk = set ? buckets_b : buckets;
-        uint32_t *out = j.d_out_wire + set * WU;
+        uint32_t *out = j.d_out_wire ? j.d_out_wire + set * WU : nullptr;      // nullptr: window sums only (no Horner)
         if constexpr (W == 8) msm_launch_reduce_g1(c, bk, g, s1, s2, wsum, out, nred);
         else msm_launch_reduce_g2(c, bk, g, s1, s2, wsum, out, nred);
         c->launches += 3;
     }
     prof_end(c, P2B_PROF_MSM_REDUCE, (int)(3 * nsets));
+    c->msm_last_wsum = wsum;            // window sums of the (last) set: W_w = sum_i digit_w(k_i) P_i
+    c->msm_last_nwin = g.nwin;
     P2B_CUDA(c, cudaGetLastError());
     return P2B_OK;
 }

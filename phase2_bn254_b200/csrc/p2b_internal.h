@@ -36,7 +36,15 @@ struct Ctx {
     unsigned long long *d_err = nullptr;   // device error word
     unsigned long long *h_err = nullptr;   // pinned mirror
     // growable device scratch
-    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, msm_f, fft_tw_dir[2], gtable, gfft;
+    DevBuf jac, prefix, stage_in[2], stage_out[2], scal, tables, misc, msm_a, msm_b, msm_c, msm_d, msm_e, msm_f, fft_tw_dir[2], gtable, gfft, probe;
+    // per-window sums of the last MSM (device, XYZZ): read by the G2 subgroup probe (msm_g2.cu)
+    uint32_t *msm_last_wsum = nullptr;
+    uint32_t msm_last_nwin = 0;
+    // G2 subgroup probe (g2_subgroup_probe): ChaCha20 key from the host CSPRNG (drawn at first use), running coefficient index
+    uint32_t probe_key[8] = {};
+    bool probe_key_set = false;
+    uint64_t probe_ctr = 0;
+    uint64_t probes = 0;                 // probes launched so far (p2b_g2_probe_count)
     // pinned staging rings + copy threads for pageable caller buffers (hostio.cu), created on first use
     HostIO *io = nullptr;
     cudaEvent_t ev[8] = {};
@@ -93,6 +101,9 @@ struct ScalarSpec {
 // d_in / d_out: device buffers holding n encodings.  Work is queued on c->stream; errors land in c->d_err.
 int launch_batch_mul(Ctx *c, int g2, const void *d_in, void *d_out, size_t n, const ScalarSpec &sc, int in_enc,
                      int out_enc, int flags, uint64_t err_index_base);
+// Queues a proof that all n G2 points (device; uncompressed wire or RAW_MONT_LE) lie in the order-r subgroup: *d_route is a
+// device word that reads 0 afterwards if they do, non-zero if the batch has to take the exact path (msm_g2.cu).
+int g2_subgroup_probe(Ctx *c, const void *d_points, size_t n, int enc, uint64_t err_base, uint32_t **d_route);
 size_t enc_size(int g2, int enc);
 int read_scalar_be(const uint8_t *be, uint32_t k[8]);   // false if >= r
 

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("P2B_LIB") or os.path.join(_HERE, "libp2b.so")   # P2B
 OK, EARG, EDECODE, EINFINITY_IN, EINFINITY_OUT, ECUDA = range(6)
 DEC_NOT_ON_CURVE, DEC_COORDINATE, DEC_UNEXPECTED_INFORMATION, DEC_UNEXPECTED_COMPRESSION_MODE = 1, 2, 3, 4
 ENC_UNCOMPRESSED, ENC_COMPRESSED, ENC_RAW_MONT_LE = 0, 1, 2
-CHECK_INPUT, REJECT_INFINITY, G2_SUBGROUP = 1, 2, 4
+CHECK_INPUT, REJECT_INFINITY, G2_SUBGROUP, G2_EXACT = 1, 2, 4, 8
 G1, G2 = 0, 1
 
 # every symbol include/p2b.h declares (tests/test_abi.py checks the header and this list agree)
@@ -33,6 +33,7 @@ SYMBOLS = [
     "p2b_rng_g2", "p2b_host_g1_mul", "p2b_host_g2_mul", "p2b_pairing_constants", "p2b_io_stats",
     "p2b_g1_msm_pair", "p2b_g2_msm_pair", "p2b_g1_power_pairs", "p2b_g2_power_pairs", "p2b_random_scalars", "p2b_phase2_contribute_sharded",
     "p2b_g1_group_fft_scaled", "p2b_g2_group_fft_scaled", "p2b_g1_gfft_stage", "p2b_g2_gfft_stage", "p2b_fr_root_of_unity", "p2b_selftest_field",
+    "p2b_g2_probe_stats",
 ]
 PROF_BATCH_MUL, PROF_NORMALIZE, PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_FFT_PASS = range(6)
 
@@ -71,6 +72,7 @@ def load():
     lib.p2b_launch_count.argtypes = [vp]
     lib.p2b_launch_count.restype = u64
     lib.p2b_version.restype = ctypes.c_char_p
+    lib.p2b_g2_probe_stats.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(i32)]
     for g in ("g1", "g2"):
         for suffix in ("", "_dev"):
             getattr(lib, "p2b_%s_batch_mul%s" % (g, suffix)).argtypes = [vp, u8p, u8p, sz, u8p, sz, i32, i32, i32]
@@ -276,6 +278,12 @@ class Context:
     @property
     def launch_count(self):
         return self.lib.p2b_launch_count(self.h)
+
+    def g2_probe_stats(self):
+        """(batches probed so far, verdict of the last probe: 0 = subgroup proven / split path, 1 = exact path, -1 = none)"""
+        n, v = ctypes.c_uint64(0), ctypes.c_int(0)
+        self._check(self.lib.p2b_g2_probe_stats(self.h, ctypes.byref(n), ctypes.byref(v)))
+        return n.value, v.value
 
     def sync(self):
         self._check(self.lib.p2b_sync(self.h))

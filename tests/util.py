@@ -153,3 +153,34 @@ class OracleCtx:
         import numpy as np
         d = len(bytes(np.asarray(points))) // (128 if group else 64)
         return self.group_fft_scaled(group, points, inverse, d.bit_length() - 1)
+
+
+# ---- points of the twist E'(Fq2) OUTSIDE the order-r subgroup (the reference decodes them without complaint, ec.rs:1145-1213)
+G2_COFACTOR = 2 * Q_MOD - R_MOD                       # ec.rs:1347-1357; = 10069 * 5864401 * 1875725156269 * (a 177-bit prime)
+G2_COFACTOR_SMALL_PRIME = 10069
+
+
+def twist_points_outside_subgroup(n, seed, small_order=False):
+    """n uncompressed G2 encodings of curve points that are not in the order-r subgroup, built with the big-int reference
+    (oracle/bn254_ref.py).  small_order: each point is S + T with S in the subgroup and T of order 10069, the smallest
+    prime factor of the cofactor -- the hardest case for a randomised membership test."""
+    import bn254_ref as ref
+    rng = random.Random(seed)
+    out = []
+    while len(out) < n:
+        x = (rng.randrange(Q_MOD), rng.randrange(Q_MOD))
+        y = ref.f2_sqrt(ref.f2_add(ref.f2_mul(ref.f2_sqr(x), x), ref.B_G2))
+        if y is None:
+            continue
+        p = (x, y)
+        assert ref.G2.on_curve(p)
+        if small_order:
+            t = ref.G2.mul(p, R_MOD * (G2_COFACTOR // G2_COFACTOR_SMALL_PRIME))
+            if t is None:
+                continue
+            assert ref.G2.mul(t, G2_COFACTOR_SMALL_PRIME) is None
+            p = ref.G2.add(ref.G2.mul(ref.G2_GEN, rng.randrange(1, R_MOD)), t)
+        if ref.G2.mul(p, R_MOD) is None:
+            continue
+        out.append(ref.g2_encode(p, False))
+    return b"".join(out)
