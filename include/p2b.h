@@ -139,7 +139,7 @@ uint64_t p2b_pot_accumulator_size(uint32_t size_log2, int compressed);
  * (hash of the challenge) and the trailing public key stay with the caller (compute_constrained.rs:155-161,207-209).
  * [shard_index, shard_count): this process transforms only its contiguous share of every section (one process per
  * GPU; shards write disjoint byte ranges of `response`); pass 0, 1 for the whole file.
- * check_input: 0 / 1 = CheckForCorrectness::{No, Yes}; may be OR-ed with P2B_G2_SUBGROUP (see the flag). */
+ * check_input: 0 / 1 = CheckForCorrectness::{No, Yes}; may be OR-ed with P2B_G2_SUBGROUP / P2B_G2_EXACT (see the flags). */
 int p2b_pot_transform(p2b_ctx *ctx, const uint8_t *challenge, uint64_t challenge_len, uint8_t *response,
                       uint64_t response_len, uint32_t size_log2, uint32_t batch_size, int in_compressed,
                       int out_compressed, int check_input, const uint8_t tau_be[32], const uint8_t alpha_be[32],
@@ -254,7 +254,7 @@ int p2b_fr_root_of_unity(uint32_t log_d, int inverse, uint8_t out_be[32]);
  * response layout, compressed; the 64-byte hash prefix included) to the image of the file phase1radix2m{m}:
  * alpha_g1 | beta_g1 | beta_g2 | coeffs_g1[d] | coeffs_g2[d] | alpha_coeffs_g1[d] | beta_coeffs_g1[d] | h[d-1], all
  * uncompressed, d = 2^m (reader: phase2/src/parameters.rs:182-217).  p2b_pot_radix_file_size(m) = 192 + 384 d bytes.
- * check_input = CheckForCorrectness of the deserialisation (the binary uses Yes); flags: 0 or P2B_G2_SUBGROUP. */
+ * check_input = CheckForCorrectness of the deserialisation (the binary uses Yes); flags: 0, P2B_G2_SUBGROUP or P2B_G2_EXACT. */
 uint64_t p2b_pot_radix_file_size(uint32_t m);
 int p2b_pot_prepare_phase2(p2b_ctx *ctx, const uint8_t *accumulator, uint64_t accumulator_len, uint32_t size_log2,
                            int compressed_input, int check_input, uint32_t m, uint8_t *out, uint64_t out_len, int flags);

@@ -273,7 +273,7 @@ static int pot_transform(Ctx *c, const uint8_t *challenge, uint64_t challenge_le
     const uint64_t g1i = in_c ? 32 : 64, g2i = in_c ? 64 : 128, g1o = out_c ? 32 : 64, g2o = out_c ? 64 : 128;
     // section order in both files: TauG1, TauG2, AlphaG1, BetaG1, BetaG2 (batched_accumulator.rs:87-94,96-178)
     const Section sections[4] = {{0, powers_g1, 0}, {1, powers, 0}, {0, powers, 1}, {0, powers, 2}};
-    const int flags = ((check & 1) ? P2B_CHECK_INPUT : 0) | P2B_REJECT_INFINITY | (check & P2B_G2_SUBGROUP);
+    const int flags = ((check & 1) ? P2B_CHECK_INPUT : 0) | P2B_REJECT_INFINITY | (check & (P2B_G2_SUBGROUP | P2B_G2_EXACT));
     int rc = begin_call(c);
     if (rc) return rc;
     uint64_t ioff = 64, ooff = 64;

@@ -175,7 +175,7 @@ template <class F> static int group_fft_dev(Ctx *c, GfftArea<F> &a, uint32_t log
             memset(&sc, 0, sizeof sc);
             sc.mode = 0;
             sc.d_scalars = a.S;
-            if ((rc = launch_batch_mul(c, g2, second, a.M, nb, sc, ENC_RAW_MONT_LE, ENC_RAW_MONT_LE, flags & P2B_G2_SUBGROUP, 0))) return rc;
+            if ((rc = launch_batch_mul(c, g2, second, a.M, nb, sc, ENC_RAW_MONT_LE, ENC_RAW_MONT_LE, flags & (P2B_G2_SUBGROUP | P2B_G2_EXACT), 0))) return rc;
             second = a.M;
         }
         k_gscatter<F><<<grid_for(c, nb), 128, 0, c->stream>>>(a.X, a.N, second, log_d, s);
@@ -189,7 +189,7 @@ template <class F> static int group_fft_dev(Ctx *c, GfftArea<F> &a, uint32_t log
         sc.mode = 1;
         memcpy(sc.k, ninv, 32);
     } else sc.mode = 3;
-    if ((rc = launch_batch_mul(c, g2, a.N, d_out, d, sc, ENC_RAW_MONT_LE, out_enc, flags & P2B_G2_SUBGROUP, 0))) return rc;
+    if ((rc = launch_batch_mul(c, g2, a.N, d_out, d, sc, ENC_RAW_MONT_LE, out_enc, flags & (P2B_G2_SUBGROUP | P2B_G2_EXACT), 0))) return rc;
     P2B_CUDA(c, cudaGetLastError());
     return P2B_OK;
 }
@@ -266,7 +266,7 @@ template <class F> static int gfft_stage_host(Ctx *c, int g2, const uint8_t *pa,
             if (!read_scalar_be(w_be, sc.tau)) return ctx_fail(c, P2B_EARG, "twiddle base not canonical");
             sc.coeff[0] = 1;
         }
-        if ((rc = launch_batch_mul(c, g2, a.N + n * WU, so + n * osz, n, sc, ENC_RAW_MONT_LE, out_enc, flags & P2B_G2_SUBGROUP, 0))) return rc;
+        if ((rc = launch_batch_mul(c, g2, a.N + n * WU, so + n * osz, n, sc, ENC_RAW_MONT_LE, out_enc, flags & (P2B_G2_SUBGROUP | P2B_G2_EXACT), 0))) return rc;
         if ((rc = io_d2h(c, out_diff, so + n * osz, n * osz, c->stream))) return rc;
     }
     return ctx_collect_error(c);

@@ -119,3 +119,38 @@ def test_default_threshold_2p17_points(ctx, oracle):
     assert ctx.g2_probe_stats() == (before + 4, 1)
     assert got[at * 128:(at + 1) * 128].tobytes() == oracle.batch_mul(1, bad, be(a), threads=1)
     assert np.array_equal(got[:at * 128], p1[:at * 128]) and np.array_equal(got[(at + 1) * 128:], p1[(at + 1) * 128:])
+
+
+def test_transform_and_group_fft_with_probed_g2_sections(ctx, oracle, probe_small):
+    """`transform` (TauG2 section, tau-powers shape inside the chunk pipeline, compressed and uncompressed input) and a G2 group
+    FFT with the probe active at these sizes: the response / the transform equal the oracle's."""
+    from phase2_bn254_b200.powersoftau import BatchedAccumulator, CeremonyParams, PrivateKey
+    tau, alpha, beta = 0x1111 ** 17 % R_MOD, 0x2222 ** 13 % R_MOD, 0x3333 ** 11 % R_MOD
+    size, batch = 8, 64
+    params = CeremonyParams(size, batch)
+    ch0 = oracle.pot_generate_initial(size)
+    ch1c = oracle.pot_transform(ch0, size, batch, be(tau), be(alpha), be(beta), out_compressed=True, threads=8)
+    ch1 = oracle.pot_transform(ch0, size, batch, be(tau), be(alpha), be(beta), out_compressed=False, threads=8)
+    key = PrivateKey(alpha, beta, tau)
+    for in_c, src in ((False, ch1), (True, ch1c)):
+        exp = oracle.pot_transform(src, size, batch, be(alpha), be(beta), be(tau), in_c, True, True, threads=8)
+        out = np.zeros(len(exp), dtype=np.uint8)
+        before, _ = ctx.g2_probe_stats()
+        BatchedAccumulator.transform(np.frombuffer(src, dtype=np.uint8), out, in_c, True, True, key, params, ctx=ctx)
+        after, verdict = ctx.g2_probe_stats()
+        assert after > before and verdict == 0
+        assert out[64:].tobytes() == exp[64:], in_c
+    # one G2 point of the challenge replaced by a point outside the subgroup: still the reference's bytes (exact path)
+    bad = twist_points_outside_subgroup(1, seed=52, small_order=True)
+    buf = bytearray(ch1)
+    off = 64 + params.powers_g1_length * 64 + 37 * 128
+    buf[off:off + 128] = bad
+    exp = oracle.pot_transform(bytes(buf), size, batch, be(alpha), be(beta), be(tau), False, True, True, threads=8)
+    out = np.zeros(len(exp), dtype=np.uint8)
+    BatchedAccumulator.transform(np.frombuffer(bytes(buf), dtype=np.uint8), out, False, True, True, key, params, ctx=ctx)
+    assert out[64:].tobytes() == exp[64:]
+    d = 256
+    pts = random_points(oracle, 1, d, seed=53)
+    got = ctx.group_fft(1, pts, True)
+    exp = ctx.group_fft(1, pts, True, flags=8)                 # P2B_G2_EXACT: the path the earlier rounds checked against the definition
+    assert np.array_equal(got, exp)

@@ -132,3 +132,39 @@ def test_glv_constants():
     a1, b1 = 0x89d3256894d213e3, -0x6f4d8248eeb859fc8211bbeb7d4f1128
     a2, b2 = 0x6f4d8248eeb859fd0be4e1541221250b, 0x89d3256894d213e3
     assert (a1 + b1 * LAMBDA) % R_MOD == 0 and (a2 + b2 * LAMBDA) % R_MOD == 0
+
+
+def test_g2_cofactor_structure_behind_the_subgroup_probe():
+    """The facts csrc/msm_g2.cu `g2_subgroup_probe` rests on, checked with the big-int reference: #E'(Fq2) = r h with
+    h = 2q - r (ec.rs:1347-1357) = 10069 * 5864401 * 1875725156269 * p177 and gcd(r, h) = 1, so [r]W = O exactly for the
+    points of the order-r subgroup; a point with a cofactor component of the smallest possible order (10069) is on the
+    curve, is not killed by r, and a random combination hiding it is not killed either unless its coefficient is a multiple
+    of 10069; sums of subgroup points stay in the subgroup."""
+    import math
+    import random
+
+    from util import G2_COFACTOR, G2_COFACTOR_SMALL_PRIME, twist_points_outside_subgroup
+    assert G2_COFACTOR == 0x30644e72e131a029b85045b68181585e06ceecda572a2489345f2299c0f9fa8d
+    p177 = 197620364512881247228717050342013327560683201906968909
+    assert G2_COFACTOR == 10069 * 5864401 * 1875725156269 * p177 and math.gcd(G2_COFACTOR, R_MOD) == 1
+    for p in (10069, 5864401, 1875725156269, p177):
+        assert pow(2, p - 1, p) == 1 and pow(3, p - 1, p) == 1          # (Fermat tests; primality proper: tools / DESIGN)
+    assert all(G2_COFACTOR % d for d in range(2, 10069))               # 10069 is the smallest prime factor
+    assert ref.G2.mul(ref.G2_GEN, R_MOD) is None
+    bad = ref.g2_decode(twist_points_outside_subgroup(1, seed=3, small_order=True), False)
+    assert ref.G2.on_curve(bad) and ref.G2.mul(bad, R_MOD) is not None
+    t = ref.G2.mul(bad, R_MOD)                                         # [r](S + T) = [r]T, of order 10069
+    assert ref.G2.mul(t, G2_COFACTOR_SMALL_PRIME) is None
+    rng = random.Random(5)
+    honest = [ref.G2.mul(ref.G2_GEN, rng.randrange(1, R_MOD)) for _ in range(3)]
+
+    def combo(points, coeffs):
+        acc = None
+        for p, c in zip(points, coeffs):
+            acc = ref.G2.add(acc, ref.G2.mul(p, c))
+        return acc
+    coeffs = [rng.randrange(1 << 15) for _ in range(4)]
+    assert ref.G2.mul(combo(honest, coeffs), R_MOD) is None
+    for c in (1, 12345, 10068, 10070, 2 * 10069 + 1):
+        assert ref.G2.mul(combo(honest + [bad], coeffs[:3] + [c]), R_MOD) is not None
+    assert ref.G2.mul(combo(honest + [bad], coeffs[:3] + [3 * 10069]), R_MOD) is None     # the 1-in-10069 blind spot of ONE sum
