@@ -47,7 +47,7 @@ int launch_batch_mul(Ctx *c, int g2, const void *d_in, void *d_out, size_t n, co
     if (in_enc < 0 || in_enc > 2 || out_enc < 0 || out_enc > 2) return ctx_fail(c, P2B_EARG, "bad encoding");
     if (g2 && (flags & P2B_G2_SUBGROUP) && !(flags & P2B_G2_EXACT))
         return launch_batch_mul_g2_glv(c, d_in, d_out, n, sc, in_enc, out_enc, flags, err_index_base, BM_ALL, nullptr, 0);
-    if (g2 && sc.mode != 3 && !(flags & P2B_G2_EXACT) && n >= g2_probe_min()) {
+    if (g2 && sc.mode != 3 && !(flags & P2B_G2_EXACT) && n >= g2_probe_min() && g2_probe_ready(c)) {
         // Large G2 batch without the caller's promise: prove subgroup membership of the whole batch on the device (msm_g2.cu),
         // queue the split kernel AND the exact kernel, and let the verdict word pick the one that runs.
         int rc;

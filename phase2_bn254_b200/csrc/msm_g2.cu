@@ -25,15 +25,22 @@ int msm_typed_g2(Ctx *c, const MsmJob &j) { return msm_typed<Fq2>(c, j); }
 // the decode kernel, because sums of off-curve points are not group sums.  The coefficients come from ChaCha20 under a key
 // drawn from the host's CSPRNG when the context first needs it; the verdict stays on the device (a word that the two
 // `k_batch_mul` launches of the caller read), so the chunk pipeline never waits for the host.
-int g2_subgroup_probe(Ctx *c, const void *d_points, size_t n, int enc, uint64_t err_base, uint32_t **d_route) {
-    if (!c->probe_key_set) {
+// Draws the ChaCha20 key of the probe from the host's CSPRNG (once per context).  false: no entropy source -- the caller then
+// takes the exact path, which needs no randomness.
+bool g2_probe_ready(Ctx *c) {
+    if (c->probe_key_set) return true;
+    try {
         std::random_device rd;                      // /dev/urandom (libstdc++)
         for (int i = 0; i < 8; i++) c->probe_key[i] = rd();
-        if (const char *e = getenv("P2B_G2_PROBE_KEY")) {       // test hook: a fixed key makes a run reproducible
-            for (int i = 0; i < 8; i++) c->probe_key[i] = (uint32_t)strtoul(e, nullptr, 0) + 0x9e3779b9u * (uint32_t)i;
-        }
-        c->probe_key_set = true;
+    } catch (...) {
+        return false;
     }
+    c->probe_key_set = true;
+    return true;
+}
+
+int g2_subgroup_probe(Ctx *c, const void *d_points, size_t n, int enc, uint64_t err_base, uint32_t **d_route) {
+    if (!g2_probe_ready(c)) return ctx_fail(c, P2B_EARG, "g2 subgroup probe: no entropy source");
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     int cw = (int)(0.6 * lg + 3.5);                 // the MSM's own window width for n terms (msm_geometry), kept within 14 .. 16

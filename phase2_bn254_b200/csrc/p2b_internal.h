@@ -103,6 +103,7 @@ int launch_batch_mul(Ctx *c, int g2, const void *d_in, void *d_out, size_t n, co
                      int out_enc, int flags, uint64_t err_index_base);
 // Queues a proof that all n G2 points (device; uncompressed wire or RAW_MONT_LE) lie in the order-r subgroup: *d_route is a
 // device word that reads 0 afterwards if they do, non-zero if the batch has to take the exact path (msm_g2.cu).
+bool g2_probe_ready(Ctx *c);     // the probe's coefficient key could be drawn from the host CSPRNG
 int g2_subgroup_probe(Ctx *c, const void *d_points, size_t n, int enc, uint64_t err_base, uint32_t **d_route);
 size_t enc_size(int g2, int enc);
 int read_scalar_be(const uint8_t *be, uint32_t k[8]);   // false if >= r
