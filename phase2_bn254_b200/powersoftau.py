@@ -261,6 +261,38 @@ class BatchedAccumulator:
             raise
 
 
+def contribute_challenge(input_map, output_map, rng, parameters, input_is_compressed=False, compress_the_output=True,
+                         check_input_for_correctness=False, ctx=None, overlap=True, g2_in_subgroup=False):
+    """One participant's step, the body of the `compute_constrained` / `beacon_constrained` binaries
+    (powersoftau/src/bin/compute_constrained.rs:140-230): hash the challenge, write that hash to the head of the response, draw
+    the key pair, transform, append the public key, hash the response.  Returns (challenge_hash, response_hash, PublicKey).
+
+    The two BLAKE2b-512 file hashes are sequential chains at about 1 GB/s on one host core (utils.rs:20-27) -- at 2^20 powers the
+    402 MB challenge alone takes longer to hash than the GPU takes to transform it.  Only the PUBLIC key depends on the challenge
+    hash (keypair.rs:64-90), the secrets come first out of the generator (keypair.rs:58-62), so with `overlap` the challenge is
+    hashed on a host thread while the GPU transforms (hashlib and the C ABI call both release the interpreter lock); the
+    generator is consumed in the reference's order either way, and the bytes written are the same (tests/test_verify_host.py).
+    The response hash needs the finished file, head included, and stays last."""
+    import threading
+    tau, alpha, beta = rng.gen_fr(), rng.gen_fr(), rng.gen_fr()
+    key = PrivateKey(tau, alpha, beta)
+    box = {}
+    hasher = threading.Thread(target=lambda: box.setdefault("h", calculate_hash(input_map)))
+    hasher.start()
+    if not overlap:
+        hasher.join()
+    try:
+        BatchedAccumulator.transform(input_map, output_map, input_is_compressed, compress_the_output, check_input_for_correctness,
+                                     key, parameters, ctx=ctx, g2_in_subgroup=g2_in_subgroup)
+    finally:
+        hasher.join()
+    digest = box["h"]
+    output_map[:64] = np.frombuffer(digest, dtype=np.uint8)
+    pubkey = public_key_for(key, rng, digest)
+    pubkey.write(output_map, compress_the_output, parameters)
+    return digest, calculate_hash(output_map), pubkey
+
+
 def _sections(parameters, compressed):
     """Byte offset and element size of the five accumulator sections (batched_accumulator.rs:96-178)."""
     p = parameters

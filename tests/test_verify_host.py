@@ -277,3 +277,40 @@ def test_scalar_bits_floor_and_system_rng():
     assert a.size == 64 * 32 and not np.array_equal(a, b)
     assert not a.reshape(64, 32)[:, :16].any() and a.reshape(64, 32)[:, 16:].any()
     assert (_random_scalars(system_rng(), 64, 253).reshape(64, 32)[:, 0] < 0x20).all()
+
+
+def test_contribute_challenge_overlapped_equals_reference_order(lib, oracle):
+    """`contribute_challenge` (the body of compute_constrained.rs:140-230) with the challenge hashed on a host thread next to the
+    transform writes the same response as the reference's order of operations, consumes the generator in keypair()'s order
+    (keypair.rs:54-103), and its output passes verify_transformation."""
+    from phase2_bn254_b200.powersoftau import (CeremonyParams, PublicKey, calculate_hash, contribute_challenge, keypair,
+                                               verify_transformation)
+    size, batch = 3, 4
+    params = CeremonyParams(size, batch)
+
+    class Ctx(OracleCtx):
+        def pot_accumulator_size(self, size, compressed):
+            p = CeremonyParams(size, 4)
+            return p.contribution_size - p.public_key_size if compressed else p.accumulator_size
+
+        def pot_transform(self, imap, omap, size, batch, tau, alpha, beta, in_c, out_c, check, shard_index=0, shard_count=1):
+            body = self.oc.pot_transform(bytes(np.asarray(imap)), size, batch, bytes(tau), bytes(alpha), bytes(beta), in_c, out_c,
+                                         bool(check & 1), threads=4)
+            omap[64:len(body)] = np.frombuffer(body, dtype=np.uint8)[64:]
+
+    ctx = Ctx(oracle)
+    ch = np.frombuffer(oracle.pot_generate_initial(size), dtype=np.uint8)
+    out = {}
+    for overlap in (True, False):
+        rs = np.zeros(params.contribution_size, dtype=np.uint8)
+        d, h, pub = contribute_challenge(ch, rs, lib.ChaChaRng([7] * 8), params, ctx=ctx, overlap=overlap)
+        assert d == calculate_hash(ch) == bytes(rs[:64]) and h == calculate_hash(rs)
+        out[overlap] = (rs.tobytes(), h, pub)
+    assert out[True] == out[False]
+    rs = np.frombuffer(out[True][0], dtype=np.uint8)
+    pub_ref, key_ref = keypair(lib.ChaChaRng([7] * 8), calculate_hash(ch))          # the reference's single call
+    assert pub_ref == out[True][2] == PublicKey.read(rs, True, params)
+    body = oracle.pot_transform(ch.tobytes(), size, batch, be(key_ref.tau), be(key_ref.alpha), be(key_ref.beta), threads=4)
+    assert rs[64:len(body)].tobytes() == body[64:]
+    assert verify_transformation(ch, rs, pub_ref, calculate_hash(ch), False, True, True, True, params, ctx=ctx,
+                                 rng=np.random.default_rng(2))
