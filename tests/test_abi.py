@@ -108,3 +108,16 @@ def test_size_helpers_and_null_ctx():
         fn.restype = ctypes.c_int
         nargs = len(fn.argtypes)
         assert fn(*([None] + [0] * (nargs - 1))) == lib.EARG, name
+
+
+def test_flag_and_code_constants_match_the_header():
+    """The binding's flag bits, encodings and error codes are the header's enum values (include/p2b.h)."""
+    import re
+    from phase2_bn254_b200 import lib
+    text = open(os.path.join(ROOT, "include", "p2b.h")).read()
+    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(P2B_[A-Z0-9_]+)\s*=\s*(\d+)", text)}
+    for name in ("CHECK_INPUT", "REJECT_INFINITY", "G2_SUBGROUP", "G2_EXACT", "ENC_UNCOMPRESSED", "ENC_COMPRESSED", "ENC_RAW_MONT_LE",
+                 "EARG", "EDECODE", "EINFINITY_IN", "EINFINITY_OUT", "DEC_NOT_ON_CURVE", "DEC_COORDINATE",
+                 "DEC_UNEXPECTED_INFORMATION", "DEC_UNEXPECTED_COMPRESSION_MODE"):
+        assert getattr(lib, name) == vals["P2B_" + name], name
+    assert vals["P2B_G2_EXACT"] == 8 and vals["P2B_G2_SUBGROUP"] == 4
