@@ -35,4 +35,12 @@ if what == "msm_g2":
     p = bench.make_points(torch, np, ctx, 1, n, 1, dev)
     s = bench.make_scalars(torch, n, 2, dev)
     print(ctx.msm_dev(1, p.data_ptr(), s.data_ptr(), n)[:8].hex())
+if what == "g2probe":                                   # one probed G2 batch_exp at 2^20 points (launch list of the probe)
+    n = 1 << 20
+    p = bench.make_points(torch, np, ctx, 1, n, 1, dev)
+    o = torch.empty(n * 128, dtype=torch.uint8, device=dev)
+    torch.cuda.nvtx.range_push("probed_batch")
+    ctx.batch_mul_dev(1, p.data_ptr(), o.data_ptr(), n, k); ctx.sync()
+    torch.cuda.nvtx.range_pop()
+    print(ctx.g2_probe_stats())
 print("done", what)
