@@ -1,6 +1,7 @@
 // msm_g2.cu -- G2 (Fq2) instantiation of the Pippenger MSM kernels, and the batch subgroup probe built on them.
 #include <cstdio>
 #include <random>
+#include <sys/random.h>
 #include "msm_impl.cuh"
 
 namespace p2b {
@@ -23,17 +24,20 @@ int msm_typed_g2(Ctx *c, const MsmJob &j) { return msm_typed<Fq2>(c, j); }
 // 2^(c-1)) consecutive integers, c = 14 .. 16.  A point outside G2 therefore survives all 8 tests with probability
 // <= 2^-104; points that are not on the curve at all (only possible without P2B_CHECK_INPUT) are caught deterministically by
 // the decode kernel, because sums of off-curve points are not group sums.  The coefficients come from ChaCha20 under a key
-// drawn from the host's CSPRNG when the context first needs it; the verdict stays on the device (a word that the two
+// drawn from the kernel's CSPRNG (getrandom) when the context first needs it; the verdict stays on the device (a word that the two
 // `k_batch_mul` launches of the caller read), so the chunk pipeline never waits for the host.
 // Draws the ChaCha20 key of the probe from the host's CSPRNG (once per context).  false: no entropy source -- the caller then
 // takes the exact path, which needs no randomness.
 bool g2_probe_ready(Ctx *c) {
     if (c->probe_key_set) return true;
-    try {
-        std::random_device rd;                      // /dev/urandom (libstdc++)
-        for (int i = 0; i < 8; i++) c->probe_key[i] = rd();
-    } catch (...) {
-        return false;
+    if (getrandom(c->probe_key, sizeof c->probe_key, 0) != (ssize_t)sizeof c->probe_key) {     // the kernel's CSPRNG
+        try {
+            std::random_device rd;                  // fallback: /dev/urandom through libstdc++
+            if (rd.entropy() == 0.0) return false;  // a deterministic engine is no source of unpredictable coefficients
+            for (int i = 0; i < 8; i++) c->probe_key[i] = rd();
+        } catch (...) {
+            return false;
+        }
     }
     c->probe_key_set = true;
     return true;
